@@ -1,0 +1,531 @@
+"""Host-side mirror of the reference's solver interface, on top of the C ABI (include/gsb200.h).
+
+The reference is Julia; its toolchain is absent here, so this Python layer plays the role of the
+Julia shim (gridapsolvers.jl_b200/julia/GridapSolversB200.jl binds the same entry points with
+ccall): same names, argument meaning and error behaviour as the reference's
+`Gridap.Algebra.LinearSolver` API -- `symbolic_setup / numerical_setup / numerical_setup! /
+solve!` (Julia's `f!` is spelled `f_`), solver constructors with the reference's keyword
+defaults, and the public `solver.log :: ConvergenceLog` filled after every solve.
+
+Reference (paths relative to /root/reference/src):
+  CGSolver               LinearSolvers/Krylov/CGSolvers.jl:10-23
+  GMRESSolver            LinearSolvers/Krylov/GMRESSolvers.jl:16-29
+  FGMRESSolver           LinearSolvers/Krylov/FGMRESSolvers.jl:17-30
+  MINRESSolver           LinearSolvers/Krylov/MINRESSolvers.jl:11-20
+  JacobiLinearSolver     LinearSolvers/JacobiLinearSolvers.jl:6
+  RichardsonSmoother     LinearSolvers/RichardsonSmoothers.jl:20-38
+  LinearSolverFromSmoother LinearSolvers/LinearSolverFromSmoothers.jl:1-3
+  IdentitySolver         LinearSolvers/IdentityLinearSolvers.jl:2
+  GMGLinearSolver        LinearSolvers/GMGLinearSolvers.jl:48-69
+  BlockTriangularSolver  BlockSolvers/BlockTriangularSolvers.jl:26-58
+  BlockDiagonalSolver    BlockSolvers/BlockDiagonalSolvers.jl:22-45
+  SolverTolerances / ConvergenceLog  SolverInterfaces/{SolverTolerances,ConvergenceLogs}.jl
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import numpy as np
+
+from . import _lib
+from ._lib import c_p, check
+
+GSB_FMT_CSR, GSB_FMT_CSC = 0, 1
+SOLVER_CONVERGED_ATOL, SOLVER_CONVERGED_RTOL, SOLVER_DIVERGED_MAXITER, SOLVER_DIVERGED_BREAKDOWN = 0, 1, 2, 3
+_MODES = {"preconditioner": 0, "solver": 1}
+_CYCLES = {"v_cycle": 0, "w_cycle": 1, "f_cycle": 2}
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(c_p)
+
+
+# --------------------------------------------------------------------------- context
+
+
+class Context:
+    """One part of a PartitionedArrays distribution == one process == one B200."""
+
+    _default = None
+
+    def __init__(self, device: int = 0, nranks: int = 1, rank: int = 0, nccl_id: bytes | None = None):
+        L = _lib.lib()
+        h = c_p()
+        idbuf = ctypes.create_string_buffer(nccl_id, 128) if nccl_id is not None else None
+        check(L.gsb_init(device, nranks, rank, idbuf, ctypes.byref(h)))
+        self.h, self.nranks, self.rank, self.device = h, nranks, rank, device
+
+    @classmethod
+    def default(cls) -> "Context":
+        if cls._default is None:
+            cls._default = Context()
+        return cls._default
+
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        check(_lib.lib().gsb_nccl_unique_id(buf))
+        return buf.raw
+
+    def set_option(self, key: str, value) -> None:
+        check(_lib.lib().gsb_set_option(self.h, key.encode(), str(value).encode()))
+
+    def synchronize(self):
+        check(_lib.lib().gsb_synchronize(self.h))
+
+    def timer_start(self):
+        check(_lib.lib().gsb_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = ctypes.c_float()
+        check(_lib.lib().gsb_timer_stop(self.h, ctypes.byref(ms)))
+        return float(ms.value)
+
+    def launch_count(self) -> int:
+        n = ctypes.c_int64()
+        check(_lib.lib().gsb_launch_count(self.h, ctypes.byref(n)))
+        return int(n.value)
+
+    def close(self):
+        if self.h:
+            _lib.lib().gsb_finalize(self.h)
+            self.h = None
+
+
+# --------------------------------------------------------------------------- PartitionedArrays mirrors
+
+
+class ExchangePlan:
+    """consistent!/assemble! cache of an index partition (neighbours + local id lists)."""
+
+    def __init__(self, ctx, n_own, n_ghost, nbr_snd, snd_ptrs, snd_ids, nbr_rcv, rcv_ptrs, rcv_ids, index_base=0):
+        self.ctx = ctx
+        a32 = lambda v: np.ascontiguousarray(v, dtype=np.int32)
+        a64 = lambda v: np.ascontiguousarray(v, dtype=np.int64)
+        self._keep = (a32(nbr_snd), a64(snd_ptrs), a64(snd_ids), a32(nbr_rcv), a64(rcv_ptrs), a64(rcv_ids))
+        k = self._keep
+        h = c_p()
+        check(_lib.lib().gsb_plan_create(ctx.h, n_own, n_ghost, len(k[0]), _ptr(k[0]), _ptr(k[1]), _ptr(k[2]),
+                                         len(k[3]), _ptr(k[3]), _ptr(k[4]), _ptr(k[5]), index_base, ctypes.byref(h)))
+        self.h, self.n_own, self.n_ghost = h, n_own, n_ghost
+
+
+class SparseMatrix:
+    """Device mirror of the local block of a PSparseMatrix (own rows x own+ghost columns)."""
+
+    def __init__(self, ctx, n_rows, n_own_cols, n_ghost_cols, ptr, idx, vals, fmt="csr", index_base=0, plan=None):
+        ptr = np.ascontiguousarray(ptr)
+        idx = np.ascontiguousarray(idx)
+        if ptr.dtype not in (np.int32, np.int64):
+            ptr = ptr.astype(np.int64)
+        idx = idx.astype(ptr.dtype, copy=False)
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        h = c_p()
+        check(_lib.lib().gsb_mat_create(ctx.h, n_rows, n_own_cols, n_ghost_cols, GSB_FMT_CSC if fmt == "csc" else GSB_FMT_CSR,
+                                        index_base, ptr.dtype.itemsize, _ptr(ptr), _ptr(idx), _ptr(vals),
+                                        plan.h if plan is not None else None, ctypes.byref(h)))
+        self.ctx, self.h, self.plan = ctx, h, plan
+        self.n_rows, self.n_own_cols, self.n_ghost_cols = n_rows, n_own_cols, n_ghost_cols
+        self.nnz = int(ptr[-1] - ptr[0])
+        self.shape = (n_rows, n_own_cols)
+
+    @classmethod
+    def from_scipy(cls, A, ctx=None, n_ghost_cols=0, plan=None):
+        """Serial (or local-block) matrix from a scipy CSR/CSC matrix."""
+        import scipy.sparse as sp
+
+        ctx = ctx or Context.default()
+        if sp.isspmatrix_csc(A):
+            return cls(ctx, A.shape[0], A.shape[1] - n_ghost_cols, n_ghost_cols, A.indptr, A.indices, A.data, fmt="csc", plan=plan)
+        A = sp.csr_matrix(A)
+        return cls(ctx, A.shape[0], A.shape[1] - n_ghost_cols, n_ghost_cols, A.indptr, A.indices, A.data, fmt="csr", plan=plan)
+
+    def update_values(self, vals):
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        assert vals.shape[0] == self.nnz
+        check(_lib.lib().gsb_mat_update_values(self.h, _ptr(vals)))
+
+
+class BlockSparseMatrix:
+    """BlockMatrix of SparseMatrix blocks acting on concatenated vectors (C5)."""
+
+    def __init__(self, blocks, ctx=None):
+        self.blocks = blocks
+        nb = len(blocks)
+        first = next(b for row in blocks for b in row if b is not None)
+        self.ctx = ctx or first.ctx
+        arr = (c_p * (nb * nb))(*[(b.h if b is not None else None) for row in blocks for b in row])
+        h = c_p()
+        check(_lib.lib().gsb_block_mat_create(self.ctx.h, nb, arr, ctypes.byref(h)))
+        self.h, self.plan = h, None
+        nr, nc, ng, nnz = (ctypes.c_int64() for _ in range(4))
+        check(_lib.lib().gsb_mat_info(h, ctypes.byref(nr), ctypes.byref(nc), ctypes.byref(ng), ctypes.byref(nnz)))
+        self.n_rows, self.n_own_cols, self.n_ghost_cols, self.nnz = nr.value, nc.value, 0, nnz.value
+        self.shape = (self.n_rows, self.n_own_cols)
+
+    def __getitem__(self, i):
+        return self.blocks[i]
+
+
+class Vector:
+    """Device mirror of the local part of a PVector: own values first, ghost values after."""
+
+    def __init__(self, ctx, n_own, n_ghost=0, h=None):
+        if h is None:
+            h = c_p()
+            check(_lib.lib().gsb_vec_create(ctx.h, n_own, n_ghost, ctypes.byref(h)))
+        self.ctx, self.h, self.n_own, self.n_ghost = ctx, h, n_own, n_ghost
+
+    def set(self, values):
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        check(_lib.lib().gsb_vec_set(self.h, _ptr(v), v.shape[0]))
+        return self
+
+    def get(self) -> np.ndarray:
+        out = np.empty(self.n_own)
+        check(_lib.lib().gsb_vec_get(self.h, _ptr(out), self.n_own))
+        return out
+
+    def get_local(self) -> np.ndarray:
+        out = np.empty(self.n_own + self.n_ghost)
+        check(_lib.lib().gsb_vec_get_local(self.h, _ptr(out), out.shape[0]))
+        return out
+
+    def fill(self, value):
+        check(_lib.lib().gsb_vec_fill(self.h, float(value)))
+        return self
+
+    def __del__(self):
+        try:
+            if self.h:
+                _lib.lib().gsb_vec_destroy(self.h)
+        except Exception:
+            pass
+
+
+def allocate_in_domain(A) -> Vector:
+    h = c_p()
+    check(_lib.lib().gsb_vec_create_domain(A.h, ctypes.byref(h)))
+    return Vector(A.ctx, A.n_own_cols, A.n_ghost_cols, h)
+
+
+def allocate_in_range(A) -> Vector:
+    h = c_p()
+    check(_lib.lib().gsb_vec_create_range(A.h, ctypes.byref(h)))
+    return Vector(A.ctx, A.n_rows, 0, h)
+
+
+def mul_(y: Vector, A, x: Vector, alpha: float = 1.0, beta: float = 0.0) -> Vector:
+    """LinearAlgebra.mul!(y,A,x[,alpha,beta])"""
+    check(_lib.lib().gsb_spmv(A.h, x.h, y.h, float(alpha), float(beta)))
+    return y
+
+
+def dot(a: Vector, b: Vector) -> float:
+    out = ctypes.c_double()
+    check(_lib.lib().gsb_dot(a.h, b.h, ctypes.byref(out)))
+    return out.value
+
+
+def norm(a: Vector) -> float:
+    out = ctypes.c_double()
+    check(_lib.lib().gsb_norm2(a.h, ctypes.byref(out)))
+    return out.value
+
+
+def axpby_(z: Vector, alpha, x: Vector, beta, y: Vector) -> Vector:
+    """z .= alpha .* x .+ beta .* y"""
+    check(_lib.lib().gsb_axpby(z.h, float(alpha), x.h, float(beta), y.h))
+    return z
+
+
+def copy_(dst: Vector, src: Vector) -> Vector:
+    check(_lib.lib().gsb_vec_copy(dst.h, src.h))
+    return dst
+
+
+def consistent_(v: Vector, plan: ExchangePlan) -> Vector:
+    check(_lib.lib().gsb_vec_consistent(v.h, plan.h if plan is not None else None))
+    return v
+
+
+# --------------------------------------------------------------------------- tolerances / logs
+
+
+class SolverTolerances:
+    """SolverInterfaces/SolverTolerances.jl:40-49"""
+
+    def __init__(self, maxiter=1000, atol=np.finfo(np.float64).eps, rtol=1e-5, dtol=math.inf):
+        self.maxiter, self.atol, self.rtol, self.dtol = int(maxiter), float(atol), float(rtol), float(dtol)
+
+
+class ConvergenceLog:
+    """SolverInterfaces/ConvergenceLogs.jl:42-60; filled from the device solve after solve!."""
+
+    def __init__(self, name, tols, verbose=0, depth=0):
+        self.name, self.tols = name, tols
+        self.num_iters = 0
+        self.residuals = np.zeros(tols.maxiter + 1)
+        self.verbose, self.depth = int(verbose), depth
+        self.flag = None
+
+    def history(self):
+        return self.residuals[: self.num_iters + 1].copy()
+
+    def _fill(self, handle):
+        n, flag = ctypes.c_int(), ctypes.c_int()
+        self.residuals[:] = 0.0
+        check(_lib.lib().gsb_solver_log(handle, ctypes.byref(n), _ptr(self.residuals), self.residuals.shape[0], ctypes.byref(flag)))
+        self.num_iters, self.flag = n.value, flag.value
+        if self.verbose > 0:  # ConvergenceLogs.jl:139-148
+            t = " " * (2 * self.depth)
+            r = self.residuals[self.num_iters]
+            print(f"{t}Solver {self.name} finished with reason {self.flag}")
+            print(t + "Iterations: %3i - Residuals: %.2e,   %.2e " % (self.num_iters, r, r / self.residuals[0] if self.residuals[0] else float('nan')))
+
+
+# --------------------------------------------------------------------------- setup protocol
+
+
+class SymbolicSetup:
+    def __init__(self, solver):
+        self.solver = solver
+
+
+class NumericalSetup:
+    """Owns the device-side NumericalSetup handle (and keeps its children alive)."""
+
+    def __init__(self, solver, handle, children=(), mat=None):
+        self.solver, self.h, self.children, self.mat = solver, handle, list(children), mat
+
+    def _logs(self):
+        if hasattr(self.solver, "log") and self.solver.log is not None:
+            self.solver.log._fill(self.h)
+        for c in self.children:
+            if c is not None:
+                c._logs()
+
+    def __del__(self):
+        try:
+            if self.h:
+                _lib.lib().gsb_solver_destroy(self.h)
+        except Exception:
+            pass
+
+
+def symbolic_setup(solver, A, x=None) -> SymbolicSetup:
+    return SymbolicSetup(solver)
+
+
+def numerical_setup(ss: SymbolicSetup, A, x=None) -> NumericalSetup:
+    return ss.solver._numerical_setup(A)
+
+
+def numerical_setup_(ns: NumericalSetup, A, x=None) -> NumericalSetup:
+    """numerical_setup!(ns,A[,x]): refresh value-dependent data after A's values changed."""
+    check(_lib.lib().gsb_solver_update(ns.h, A.h))
+    ns.mat = A
+    return ns
+
+
+def solve_(x, ns: NumericalSetup, b):
+    """solve!(x,ns,b).  x, b: device `Vector`s, or host numpy arrays of own values (the e2e path:
+    H2D of b and x, solve, D2H of x inside one C call)."""
+    L = _lib.lib()
+    if isinstance(x, np.ndarray):
+        assert x.dtype == np.float64 and b.dtype == np.float64 and x.flags.c_contiguous and b.flags.c_contiguous
+        check(L.gsb_solve_host(ns.h, _ptr(x), _ptr(b), x.shape[0]))
+    else:
+        check(L.gsb_solve(ns.h, x.h, b.h))
+    ns._logs()
+    return x
+
+
+def ldiv_(x, ns, b):
+    return solve_(x, ns, b)
+
+
+def _child(solver, A):
+    return None if solver is None else numerical_setup(symbolic_setup(solver, A), A)
+
+
+def _h(ns):
+    return None if ns is None else ns.h
+
+
+# --------------------------------------------------------------------------- solvers
+
+
+class LinearSolver:
+    log = None
+
+
+class IdentitySolver(LinearSolver):
+    def _numerical_setup(self, A):
+        h = c_p()
+        check(_lib.lib().gsb_identity_create(A.ctx.h, ctypes.byref(h)))
+        return NumericalSetup(self, h)
+
+
+class JacobiLinearSolver(LinearSolver):
+    def _numerical_setup(self, A):
+        h = c_p()
+        check(_lib.lib().gsb_jacobi_create(A.h, ctypes.byref(h)))
+        return NumericalSetup(self, h, mat=A)
+
+
+class LUSolver(LinearSolver):
+    """Gridap.Algebra.LUSolver stand-in: dense fp64 inverse on the device (coarsest GMG level)."""
+
+    def _numerical_setup(self, A):
+        h = c_p()
+        check(_lib.lib().gsb_dense_lu_create(A.h, ctypes.byref(h)))
+        return NumericalSetup(self, h, mat=A)
+
+
+class RichardsonSmoother(LinearSolver):
+    def __init__(self, M, niter: int = 1, omega: float = 1.0):
+        self.M, self.niter, self.omega = M, int(niter), float(omega)
+
+    def _numerical_setup(self, A):
+        Mns = _child(self.M, A)
+        h = c_p()
+        check(_lib.lib().gsb_richardson_create(A.h, Mns.h, self.niter, self.omega, ctypes.byref(h)))
+        return NumericalSetup(self, h, [Mns], mat=A)
+
+
+class LinearSolverFromSmoother(LinearSolver):
+    def __init__(self, smoother):
+        self.smoother = smoother
+
+    def _numerical_setup(self, A):
+        sns = _child(self.smoother, A)
+        h = c_p()
+        check(_lib.lib().gsb_from_smoother_create(A.h, sns.h, ctypes.byref(h)))
+        return NumericalSetup(self, h, [sns], mat=A)
+
+
+def Fill(value, n):
+    """FillArrays.Fill(value,n): n references to the SAME solver object (GMGLinearSolvers.jl:52)."""
+    return [value] * n
+
+
+class GMGLinearSolver(LinearSolver):
+    """GMGLinearSolver(matrices, prolongations, restrictions; ...) -- GMGLinearSolvers.jl:48-69.
+    Transfer operators are explicit sparse matrices (P, and R = P^T for mode=:residual)."""
+
+    def __init__(self, smatrices, interp, restrict, pre_smoothers=None, post_smoothers=None, coarsest_solver=None,
+                 mode="preconditioner", cycle_type="v_cycle", maxiter=100, atol=1.0e-14, rtol=1.0e-08, verbose=False):
+        n = len(smatrices)
+        if pre_smoothers is None:
+            pre_smoothers = Fill(RichardsonSmoother(JacobiLinearSolver(), 10), n - 1)
+        if post_smoothers is None:
+            post_smoothers = pre_smoothers
+        assert n - 1 == len(interp) == len(restrict) == len(pre_smoothers) == len(post_smoothers)  # @check :59
+        assert mode in _MODES and cycle_type in _CYCLES  # @check :60-61
+        self.smatrices, self.interp, self.restrict = list(smatrices), list(interp), list(restrict)
+        self.pre_smoothers, self.post_smoothers = pre_smoothers, post_smoothers
+        self.coarsest_solver = coarsest_solver if coarsest_solver is not None else LUSolver()
+        self.mode, self.cycle_type = mode, cycle_type
+        self.log = ConvergenceLog("GMG", SolverTolerances(maxiter=maxiter, atol=atol, rtol=rtol), verbose=verbose)
+
+    def _numerical_setup(self, mat):  # GMGLinearSolvers.jl:183-210
+        self.smatrices[0] = mat  # :336-340
+        sm = self.smatrices
+        n = len(sm)
+        pre = [_child(s, A) for s, A in zip(self.pre_smoothers, sm[: n - 1])]
+        post = pre if self.pre_smoothers is self.post_smoothers else [_child(s, A) for s, A in zip(self.post_smoothers, sm[: n - 1])]
+        coarse = _child(self.coarsest_solver, sm[n - 1])
+        arr = lambda objs: (c_p * max(1, len(objs)))(*[o.h for o in objs])
+        h = c_p()
+        check(_lib.lib().gsb_gmg_create(mat.ctx.h, n, arr(sm), arr(self.interp), arr(self.restrict), arr(pre), arr(post),
+                                        coarse.h, _MODES[self.mode], _CYCLES[self.cycle_type], self.log.tols.maxiter,
+                                        self.log.tols.atol, self.log.tols.rtol, ctypes.byref(h)))
+        kids = pre + ([] if post is pre else post) + [coarse]
+        return NumericalSetup(self, h, kids, mat=mat)
+
+
+class CGSolver(LinearSolver):
+    def __init__(self, Pl=None, maxiter=1000, atol=1e-12, rtol=1.0e-6, flexible=False, verbose=0, name="CG"):
+        self.Pl, self.flexible = Pl, bool(flexible)
+        self.log = ConvergenceLog(name, SolverTolerances(maxiter=maxiter, atol=atol, rtol=rtol), verbose=verbose)
+
+    def _numerical_setup(self, A):
+        Pl = _child(self.Pl, A)
+        t = self.log.tols
+        h = c_p()
+        check(_lib.lib().gsb_cg_create(A.h, _h(Pl), int(self.flexible), t.maxiter, t.atol, t.rtol, ctypes.byref(h)))
+        return NumericalSetup(self, h, [Pl], mat=A)
+
+
+class GMRESSolver(LinearSolver):
+    _create = "gsb_gmres_create"
+
+    def __init__(self, m, Pr=None, Pl=None, restart=False, m_add=1, maxiter=100, atol=1e-12, rtol=1.0e-6,
+                 verbose=False, name="GMRES"):
+        self.m, self.restart, self.m_add, self.Pr, self.Pl = int(m), bool(restart), int(m_add), Pr, Pl
+        self.log = ConvergenceLog(name, SolverTolerances(maxiter=maxiter, atol=atol, rtol=rtol), verbose=verbose)
+
+    def _numerical_setup(self, A):
+        Pr, Pl = _child(self.Pr, A), _child(self.Pl, A)
+        t = self.log.tols
+        h = c_p()
+        check(getattr(_lib.lib(), self._create)(A.h, _h(Pr), _h(Pl), self.m, int(self.restart), self.m_add, t.maxiter,
+                                                t.atol, t.rtol, ctypes.byref(h)))
+        return NumericalSetup(self, h, [Pr, Pl], mat=A)
+
+
+class FGMRESSolver(GMRESSolver):
+    _create = "gsb_fgmres_create"
+
+    def __init__(self, m, Pr, Pl=None, restart=False, m_add=1, maxiter=100, atol=1e-12, rtol=1.0e-6,
+                 verbose=False, name="FGMRES"):
+        super().__init__(m, Pr=Pr, Pl=Pl, restart=restart, m_add=m_add, maxiter=maxiter, atol=atol, rtol=rtol,
+                         verbose=verbose, name=name)
+
+
+class MINRESSolver(LinearSolver):
+    def __init__(self, Pl=None, maxiter=1000, atol=1e-12, rtol=1.0e-6, verbose=False, name="MINRES"):
+        self.Pl = Pl
+        self.log = ConvergenceLog(name, SolverTolerances(maxiter=maxiter, atol=atol, rtol=rtol), verbose=verbose)
+
+    def _numerical_setup(self, A):
+        Pl = _child(self.Pl, A)
+        t = self.log.tols
+        h = c_p()
+        check(_lib.lib().gsb_minres_create(A.h, _h(Pl), t.maxiter, t.atol, t.rtol, ctypes.byref(h)))
+        return NumericalSetup(self, h, [Pl], mat=A)
+
+
+class _BlockSolver(LinearSolver):
+    diagonal = False
+
+    def __init__(self, solvers, coeffs=None, half="upper", diag_mats=None):
+        self.solvers, self.half, self.diag_mats = list(solvers), half, diag_mats
+        nb = len(solvers)
+        self.coeffs = np.ones((nb, nb)) if coeffs is None else np.ascontiguousarray(coeffs, dtype=np.float64)
+
+    def _numerical_setup(self, A):
+        """A: BlockSparseMatrix.  Diagonal solvers are set up on A[i][i] unless diag_mats[i] overrides
+        it (MatrixBlock / BiformBlock semantics, BlockSolverInterfaces.jl:162,262)."""
+        nb = len(self.solvers)
+        dm = [(self.diag_mats[i] if (self.diag_mats and self.diag_mats[i] is not None) else A[i][i]) for i in range(nb)]
+        kids = [_child(self.solvers[i], dm[i]) for i in range(nb)]
+        blocks = (c_p * (nb * nb))(*[(A[i][j].h if A[i][j] is not None else None) for i in range(nb) for j in range(nb)])
+        sol = (c_p * nb)(*[k.h for k in kids])
+        h = c_p()
+        check(_lib.lib().gsb_block_solver_create(A.ctx.h, nb, blocks, sol, _ptr(self.coeffs), 1 if self.half == "lower" else 0,
+                                                 int(self.diagonal), ctypes.byref(h)))
+        return NumericalSetup(self, h, kids, mat=A)
+
+
+class BlockTriangularSolver(_BlockSolver):
+    pass
+
+
+class BlockDiagonalSolver(_BlockSolver):
+    diagonal = True
+
+    def __init__(self, solvers, diag_mats=None):
+        super().__init__(solvers, None, "upper", diag_mats)

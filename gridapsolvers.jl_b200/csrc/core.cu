@@ -1,0 +1,852 @@
+// core.cu -- context, device mirrors (plan / matrix / vector) and launchers of the sm_100a kernels.
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <stdexcept>
+
+#include "kernels.cuh"
+#include "ops.h"
+
+namespace gsb {
+
+static thread_local std::string g_last_error;
+
+void fail(int code, const std::string &msg) { throw Error{code, msg}; }
+
+int set_error(gsb_ctx_t ctx, const std::string &msg) {
+  g_last_error = msg;
+  if (ctx) ctx->err = msg;
+  return 0;
+}
+const std::string &last_error() { return g_last_error; }
+
+// stream kernel geometry (see kernels.cuh): 256 threads, 16384-entry ring (192 KB), 1024-entry chunks
+constexpr int ST_THREADS = 256;
+constexpr int ST_RING_LOG2 = 14;
+constexpr int ST_CHUNK_LOG2 = 10;
+constexpr int ST_SPAN_MAX = (1 << ST_RING_LOG2) / 2;
+constexpr size_t ST_SMEM = (size_t)(1 << ST_RING_LOG2) * 12 + (size_t)((1 << ST_RING_LOG2) >> ST_CHUNK_LOG2) * 8;
+constexpr int VEC_THREADS = 256;
+constexpr int EW_THREADS = 256;
+constexpr size_t PARTIALS_CAP = (size_t)1 << 20;
+
+static inline int ew_grid(gsb_ctx_t ctx, int64_t n) {
+  int64_t b = (n + EW_THREADS - 1) / EW_THREADS;
+  int64_t cap = (int64_t)ctx->num_sms * 8;
+  return (int)std::max<int64_t>(1, std::min(b, cap));
+}
+
+static inline void launched(gsb_ctx_t ctx) {
+  ctx->launches++;
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) fail(GSB_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+}
+
+}  // namespace gsb
+
+using namespace gsb;
+
+// ------------------------------------------------------------------------------------------ ctx
+int gsb_ctx_s::alloc_slots(int n) {
+  if (next_slot + n > (int)scal.n) fail(GSB_ENOMEM, "out of device scalar slots");
+  int s = next_slot;
+  next_slot += n;
+  return s;
+}
+void gsb_ctx_s::read_scalars(int slot, int n, double *out) {
+  GSB_CUDA(cudaMemcpyAsync(h_scal, scal.p + slot, sizeof(double) * n, cudaMemcpyDeviceToHost, stream));
+  GSB_CUDA(cudaStreamSynchronize(stream));
+  for (int i = 0; i < n; ++i) out[i] = h_scal[i];
+}
+double gsb_ctx_s::read_scalar(int slot) {
+  double v;
+  read_scalars(slot, 1, &v);
+  return v;
+}
+void gsb_ctx_s::allreduce_slot(int slot, int n) {
+  if (nranks > 1) GSB_NCCL(ncclAllReduce(scal.p + slot, scal.p + slot, n, ncclDouble, ncclSum, comm, stream));
+}
+ReduceOut gsb_ctx_s::reduce_out(int slot) {
+  ReduceOut r;
+  r.partials = partials.p;
+  r.ticket = ticket.p;
+  r.scal = scal.p;
+  r.slot[0] = slot;
+  r.slot[1] = slot;
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------ ops
+namespace gsb {
+
+void vec_fill(gsb_vec_s &v, double val) {
+  if (v.n_local() == 0) return;
+  if (val == 0.0) {
+    GSB_CUDA(cudaMemsetAsync(v.d, 0, sizeof(double) * v.n_local(), v.ctx->stream));
+  } else {
+    EwArgs g{};
+    // z = a*x with x := z is not a fill; use a tiny dedicated path: a*1 via has_d trick is overkill
+    std::vector<double> h((size_t)v.n_local(), val);
+    GSB_CUDA(cudaMemcpyAsync(v.d, h.data(), sizeof(double) * v.n_local(), cudaMemcpyHostToDevice, v.ctx->stream));
+    GSB_CUDA(cudaStreamSynchronize(v.ctx->stream));
+    (void)g;
+  }
+}
+
+void vec_copy(gsb_vec_s &dst, const gsb_vec_s &src) {
+  GSB_CHECK(dst.n_own == src.n_own, "copy!: own sizes differ");
+  if (dst.d == src.d || dst.n_own == 0) return;
+  GSB_CUDA(cudaMemcpyAsync(dst.d, src.d, sizeof(double) * dst.n_own, cudaMemcpyDeviceToDevice, dst.ctx->stream));
+}
+
+static void ew_launch(gsb_ctx_t ctx, EwArgs &g) {
+  if (g.n == 0) return;
+  g.scal = ctx->scal.p;
+  ew_kernel<EW_THREADS><<<ew_grid(ctx, g.n), EW_THREADS, 0, ctx->stream>>>(g);
+  launched(ctx);
+}
+
+void ew_axpby(gsb_vec_s &z, ScalarRef a, const gsb_vec_s &x, ScalarRef b, const gsb_vec_s *y, ScalarRef c,
+              const gsb_vec_s *w, bool has_d, ScalarRef d) {
+  EwArgs g{};
+  g.z = z.d; g.x = x.d; g.y = y ? y->d : nullptr; g.w = w ? w->d : nullptr;
+  g.a = a; g.b = b; g.c = c; g.d = d;
+  g.has_y = y != nullptr; g.has_w = w != nullptr; g.has_d = has_d; g.mul_xy = 0;
+  g.n = z.n_own;
+  GSB_CHECK(x.n_own == z.n_own && (!y || y->n_own == z.n_own) && (!w || w->n_own == z.n_own), "broadcast: own sizes differ");
+  ew_launch(z.ctx, g);
+}
+
+void ew_div(gsb_vec_s &z, const gsb_vec_s &x, ScalarRef d) {
+  ew_axpby(z, imm(1.0), x, imm(0.0), nullptr, imm(0.0), nullptr, true, d);
+}
+
+void ew_mul_raw(gsb_vec_s &z, const double *dvec, const gsb_vec_s &x) {
+  EwArgs g{};
+  g.z = z.d; g.x = dvec; g.y = x.d; g.mul_xy = 1; g.n = z.n_own;
+  g.a = g.b = g.c = g.d = imm(0.0);
+  ew_launch(z.ctx, g);
+}
+
+void dot(const gsb_vec_s &a, const gsb_vec_s &b, int slot) {
+  gsb_ctx_t ctx = a.ctx;
+  GSB_CHECK(a.n_own == b.n_own, "dot: own sizes differ");
+  int grid = ew_grid(ctx, std::max<int64_t>(a.n_own, 1));
+  dot_kernel<EW_THREADS><<<grid, EW_THREADS, 0, ctx->stream>>>(a.n_own, a.d, b.d, ctx->reduce_out(slot));
+  launched(ctx);
+  ctx->allreduce_slot(slot);
+}
+
+void jacobi_step(const double *invd, const gsb_vec_s &r, double omega, gsb_vec_s &dx, gsb_vec_s &x, bool x_is_zero) {
+  gsb_ctx_t ctx = r.ctx;
+  if (r.n_own == 0) return;
+  jacobi_step_kernel<EW_THREADS><<<ew_grid(ctx, r.n_own), EW_THREADS, 0, ctx->stream>>>(r.n_own, invd, r.d, omega, dx.d,
+                                                                                        x.d, x_is_zero ? 1 : 0);
+  launched(ctx);
+}
+
+void jacobi_dot(const double *invd, const gsb_vec_s &r, gsb_vec_s &z, int slot) {
+  gsb_ctx_t ctx = r.ctx;
+  int grid = ew_grid(ctx, std::max<int64_t>(r.n_own, 1));
+  jacobi_dot_kernel<EW_THREADS><<<grid, EW_THREADS, 0, ctx->stream>>>(r.n_own, invd, r.d, z.d, ctx->reduce_out(slot));
+  launched(ctx);
+  ctx->allreduce_slot(slot);
+}
+
+void cg_update(ScalarRef alpha, const gsb_vec_s &p, const gsb_vec_s &w, gsb_vec_s &x, gsb_vec_s &r, int slot) {
+  gsb_ctx_t ctx = r.ctx;
+  int grid = ew_grid(ctx, std::max<int64_t>(r.n_own, 1));
+  cg_update_kernel<EW_THREADS><<<grid, EW_THREADS, 0, ctx->stream>>>(r.n_own, alpha, p.d, w.d, x.d, r.d,
+                                                                     ctx->reduce_out(slot));
+  launched(ctx);
+  ctx->allreduce_slot(slot);
+}
+
+void inv_diag(gsb_mat_t A, double *invd) {
+  gsb_ctx_t ctx = A->ctx;
+  if (A->n_rows == 0) return;
+  int grid = (int)((A->n_rows + 255) / 256);
+  inv_diag_kernel<<<grid, 256, 0, ctx->stream>>>(A->n_rows, A->rowptr.p, A->col.p, A->val.p, invd);
+  launched(ctx);
+}
+
+// ---------------------------------------------------------------- halo exchange (consistent!)
+void consistent(gsb_vec_s &v, gsb_plan_t plan) {
+  gsb_ctx_t ctx = v.ctx;
+  if (!plan || ctx->nranks == 1) return;
+  if (plan->nbr_snd.empty() && plan->nbr_rcv.empty()) return;
+  GSB_CHECK(v.n_own == plan->n_own && v.n_ghost == plan->n_ghost, "consistent!: vector does not match the plan");
+  const int64_t nsnd = plan->snd_ptrs.back(), nrcv = plan->rcv_ptrs.back();
+  if (nsnd) {
+    int grid = (int)std::min<int64_t>((nsnd + 255) / 256, 1024);
+    pack_kernel<<<grid, 256, 0, ctx->stream>>>(nsnd, plan->snd_ids.p, v.d, plan->snd_buf.p);
+    launched(ctx);
+  }
+  GSB_NCCL(ncclGroupStart());
+  for (size_t k = 0; k < plan->nbr_rcv.size(); ++k) {
+    const int64_t off = plan->rcv_ptrs[k], cnt = plan->rcv_ptrs[k + 1] - off;
+    if (cnt) GSB_NCCL(ncclRecv(plan->rcv_buf.p + off, cnt, ncclDouble, plan->nbr_rcv[k], ctx->comm, ctx->stream));
+  }
+  for (size_t k = 0; k < plan->nbr_snd.size(); ++k) {
+    const int64_t off = plan->snd_ptrs[k], cnt = plan->snd_ptrs[k + 1] - off;
+    if (cnt) GSB_NCCL(ncclSend(plan->snd_buf.p + off, cnt, ncclDouble, plan->nbr_snd[k], ctx->comm, ctx->stream));
+  }
+  GSB_NCCL(ncclGroupEnd());
+  if (nrcv) {
+    int grid = (int)std::min<int64_t>((nrcv + 255) / 256, 1024);
+    unpack_kernel<<<grid, 256, 0, ctx->stream>>>(nrcv, plan->rcv_ids.p, plan->rcv_buf.p, v.d);
+    launched(ctx);
+  }
+}
+
+// ---------------------------------------------------------------- row kernels
+template <int G, int MODE>
+static void launch_stream(gsb_mat_t A, RowArgs &a) {
+  gsb_ctx_t ctx = A->ctx;
+  auto kern = csr_stream_kernel<G, MODE, ST_THREADS, ST_RING_LOG2, ST_CHUNK_LOG2>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
+    attr_set = true;
+  }
+  StreamArgs m{A->rowptr.p, A->col.p, A->val.p, A->cta_rows.p, A->nnz_padded};
+  kern<<<A->n_ctas, ST_THREADS, ST_SMEM, ctx->stream>>>(m, a);
+  launched(ctx);
+}
+
+template <int G, int MODE>
+static void launch_vector(gsb_mat_t A, RowArgs &a) {
+  gsb_ctx_t ctx = A->ctx;
+  const int64_t threads = A->n_rows * G;
+  const int64_t grid = std::max<int64_t>(1, (threads + VEC_THREADS - 1) / VEC_THREADS);
+  if (MODE == ROW_SPMV_DOT) GSB_CHECK((size_t)grid <= PARTIALS_CAP, "matrix too large for the vector kernel's fused dot");
+  csr_vector_kernel<G, MODE, VEC_THREADS><<<(unsigned)grid, VEC_THREADS, 0, ctx->stream>>>(A->n_rows, A->rowptr.p,
+                                                                                          A->col.p, A->val.p, a);
+  launched(ctx);
+}
+
+template <int MODE>
+static void launch_rows(gsb_mat_t A, RowArgs &a) {
+  gsb_ctx_t ctx = A->ctx;
+  if (A->n_rows == 0 && MODE != ROW_SPMV_DOT) return;
+  const std::string pref = ctx->opt("spmv", "auto");
+  const int span_rows = ST_SPAN_MAX / std::max(1, A->max_row_nnz);
+  bool stream = A->stream_ok && span_rows >= 1;
+  if (pref == "vector") stream = false;
+  else if (pref == "auto") stream = stream && A->n_rows >= (int64_t)std::stoll(ctx->opt("stream_min_rows", "65536"));
+  if (A->n_rows == 0) stream = false;
+  if (stream) {
+    switch (A->G) {
+      case 1: launch_stream<1, MODE>(A, a); break;
+      case 4: launch_stream<4, MODE>(A, a); break;
+      default: launch_stream<16, MODE>(A, a); break;
+    }
+  } else {
+    switch (A->G) {
+      case 1: launch_vector<1, MODE>(A, a); break;
+      case 4: launch_vector<4, MODE>(A, a); break;
+      default: launch_vector<16, MODE>(A, a); break;
+    }
+  }
+}
+
+static void check_gather(gsb_mat_t A, const gsb_vec_s &x, const char *what) {
+  GSB_CHECK(x.n_own == A->n_own_cols, std::string(what) + ": x own size != own columns of A");
+  GSB_CHECK(x.n_ghost >= A->n_ghost_cols || A->n_ghost_cols == 0, std::string(what) + ": x has no ghost entries for A's ghost columns");
+}
+
+gsb_vec_s view(gsb_vec_s &v, int64_t off, int64_t n) {
+  gsb_vec_s s;
+  s.ctx = v.ctx; s.n_own = n; s.n_ghost = 0; s.d = v.d + off; s.owns = false;
+  return s;
+}
+
+void spmv(gsb_mat_t A, gsb_vec_s &x, gsb_vec_s &y, double alpha, double beta) {
+  if (A->nb > 0) {  // block matrix on concatenated vectors
+    for (int i = 0; i < A->nb; ++i) {
+      gsb_vec_s yi = view(y, A->row_off[i], A->row_off[i + 1] - A->row_off[i]);
+      bool first = true;
+      for (int j = 0; j < A->nb; ++j) {
+        gsb_mat_t B = A->blocks[(size_t)i * A->nb + j];
+        if (!B) continue;
+        gsb_vec_s xj = view(x, A->col_off[j], A->col_off[j + 1] - A->col_off[j]);
+        spmv(B, xj, yi, alpha, first ? beta : 1.0);
+        first = false;
+      }
+      if (first) {
+        if (beta == 0.0) vec_fill(yi, 0.0);
+        else if (beta != 1.0) ew_axpby(yi, imm(beta), yi, imm(0.0), nullptr);
+      }
+    }
+    return;
+  }
+  check_gather(A, x, "mul!");
+  GSB_CHECK(y.n_own == A->n_rows, "mul!: y own size != rows of A");
+  GSB_CHECK(x.d != y.d, "mul!: x and y alias");
+  consistent(x, A->plan);
+  RowArgs a{};
+  a.x = x.d; a.y = y.d; a.alpha = alpha; a.beta = beta;
+  launch_rows<ROW_SPMV>(A, a);
+}
+
+void resid(gsb_mat_t A, gsb_vec_s &x, const gsb_vec_s &b, gsb_vec_s &out) {
+  if (A->nb > 0) {
+    GSB_CHECK(out.d != b.d, "block residual needs out != b");
+    spmv(A, x, out, 1.0, 0.0);
+    ew_axpby(out, imm(1.0), b, imm(-1.0), &out);
+    return;
+  }
+  check_gather(A, x, "residual");
+  GSB_CHECK(out.n_own == A->n_rows && b.n_own == A->n_rows, "residual: size mismatch");
+  GSB_CHECK(x.d != out.d, "residual: x and out alias");
+  consistent(x, A->plan);
+  RowArgs a{};
+  a.x = x.d; a.b = b.d; a.out = out.d; a.alpha = 1.0;
+  launch_rows<ROW_RESID>(A, a);
+}
+
+void sweep(gsb_mat_t A, gsb_vec_s &dx_in, gsb_vec_s &r, const double *invd, double omega, gsb_vec_s &dx_out,
+           gsb_vec_s &xacc) {
+  GSB_CHECK(A->nb == 0, "sweep: block matrices not supported");
+  check_gather(A, dx_in, "sweep");
+  GSB_CHECK(dx_in.d != dx_out.d && dx_in.d != r.d && dx_in.d != xacc.d, "sweep: aliasing");
+  consistent(dx_in, A->plan);
+  RowArgs a{};
+  a.x = dx_in.d; a.b = r.d; a.out = r.d; a.invd = invd; a.omega = omega; a.dxout = dx_out.d; a.xacc = xacc.d; a.alpha = 1.0;
+  launch_rows<ROW_SWEEP>(A, a);
+}
+
+void spmv_dot(gsb_mat_t A, gsb_vec_s &x, gsb_vec_s &y, const gsb_vec_s &dotv, int slot) {
+  gsb_ctx_t ctx = A->ctx;
+  if (A->nb > 0) {
+    spmv(A, x, y, 1.0, 0.0);
+    dot(dotv, y, slot);
+    return;
+  }
+  check_gather(A, x, "mul!");
+  GSB_CHECK(x.d != y.d, "mul!: x and y alias");
+  consistent(x, A->plan);
+  RowArgs a{};
+  a.x = x.d; a.y = y.d; a.dotv = dotv.d; a.alpha = 1.0;
+  a.red = ctx->reduce_out(slot);
+  launch_rows<ROW_SPMV_DOT>(A, a);
+  ctx->allreduce_slot(slot);
+}
+
+void spmv_add(gsb_mat_t A, gsb_vec_s &x, gsb_vec_s &y, gsb_vec_s &xacc) {
+  GSB_CHECK(A->nb == 0, "spmv_add: block matrices not supported");
+  check_gather(A, x, "mul!");
+  consistent(x, A->plan);
+  RowArgs a{};
+  a.x = x.d; a.y = y.d; a.xacc = xacc.d; a.alpha = 1.0;
+  launch_rows<ROW_SPMV_ADD>(A, a);
+}
+
+// ---------------------------------------------------------------- dense coarse solver
+void dense_inverse_rows(gsb_mat_t A, DevBuf<double> &inv_rows, int64_t &n_global, int64_t &row_off) {
+  gsb_ctx_t ctx = A->ctx;
+  GSB_CHECK(A->nb == 0, "dense LU: block matrices not supported");
+  // global numbering: own rows of rank p are [off_p, off_p + n_own_p)  (PartitionedArrays own-first gids)
+  std::vector<int64_t> counts((size_t)ctx->nranks, 0);
+  counts[(size_t)ctx->rank] = A->n_rows;
+  DevBuf<int64_t> col_gid;
+  if (ctx->nranks > 1) {
+    DevBuf<double> cnt((size_t)ctx->nranks);
+    std::vector<double> h((size_t)ctx->nranks, 0.0);
+    h[(size_t)ctx->rank] = (double)A->n_rows;
+    GSB_CUDA(cudaMemcpyAsync(cnt.p, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, ctx->stream));
+    GSB_NCCL(ncclAllReduce(cnt.p, cnt.p, h.size(), ncclDouble, ncclSum, ctx->comm, ctx->stream));
+    GSB_CUDA(cudaMemcpyAsync(h.data(), cnt.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    GSB_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int p = 0; p < ctx->nranks; ++p) counts[(size_t)p] = (int64_t)h[(size_t)p];
+  }
+  row_off = 0;
+  n_global = 0;
+  for (int p = 0; p < ctx->nranks; ++p) {
+    if (p < ctx->rank) row_off += counts[(size_t)p];
+    n_global += counts[(size_t)p];
+  }
+  GSB_CHECK(n_global <= 16384, "dense coarse solver: coarsest level too large (" + std::to_string(n_global) + " > 16384 dofs); add GMG levels");
+  GSB_CHECK(ctx->nranks > 1 || A->n_own_cols == A->n_rows, "dense LU: matrix must be square");
+  const int64_t n = n_global;
+  if (ctx->nranks > 1) {
+    // global ids of local columns: own = row_off + i, ghosts via one halo exchange of the gid vector
+    gsb_vec_s g;
+    g.ctx = ctx; g.n_own = A->n_own_cols; g.n_ghost = A->n_ghost_cols;
+    GSB_CUDA(cudaMalloc(&g.d, sizeof(double) * std::max<int64_t>(1, g.n_local())));
+    std::vector<double> h((size_t)g.n_local(), -1.0);
+    for (int64_t i = 0; i < g.n_own; ++i) h[(size_t)i] = (double)(row_off + i);
+    GSB_CUDA(cudaMemcpyAsync(g.d, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, ctx->stream));
+    consistent(g, A->plan);
+    GSB_CUDA(cudaMemcpyAsync(h.data(), g.d, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    GSB_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<int64_t> gid(h.size());
+    for (size_t i = 0; i < h.size(); ++i) gid[i] = (int64_t)h[i];
+    col_gid.alloc(gid.size());
+    GSB_CUDA(cudaMemcpyAsync(col_gid.p, gid.data(), sizeof(int64_t) * gid.size(), cudaMemcpyHostToDevice, ctx->stream));
+    GSB_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  // augmented [A | I], row-major n x 2n
+  DevBuf<double> M((size_t)n * 2 * n);
+  GSB_CUDA(cudaMemsetAsync(M.p, 0, sizeof(double) * M.n, ctx->stream));
+  if (A->n_rows) {
+    csr_to_dense_kernel<<<(unsigned)((A->n_rows + 255) / 256), 256, 0, ctx->stream>>>(
+        A->n_rows, row_off, 2 * n, A->rowptr.p, A->col.p, col_gid.p, A->val.p, M.p);
+    launched(ctx);
+  }
+  if (ctx->nranks > 1) {
+    // every rank filled its own rows only: a sum-allreduce assembles the replicated matrix (x + 0 exact)
+    size_t total = M.n, done = 0;
+    const size_t piece = (size_t)1 << 26;
+    while (done < total) {
+      size_t c = std::min(piece, total - done);
+      GSB_NCCL(ncclAllReduce(M.p + done, M.p + done, c, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+      done += c;
+    }
+  }
+  gj_set_identity_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, M.p);
+  launched(ctx);
+  DevBuf<int> piv(1);
+  DevBuf<double> pivval(1), prow((size_t)2 * n), fcol((size_t)n);
+  const unsigned gcols = (unsigned)((2 * n + 255) / 256);
+  for (int64_t k = 0; k < n; ++k) {
+    gj_pivot_kernel<<<1, 256, 0, ctx->stream>>>(n, k, M.p, piv.p, pivval.p);
+    gj_fcol_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, k, M.p, piv.p, fcol.p);
+    gj_swap_scale_kernel<<<gcols, 256, 0, ctx->stream>>>(n, k, M.p, piv.p, pivval.p, prow.p);
+    gj_eliminate_kernel<<<dim3(gcols, (unsigned)n), 256, 0, ctx->stream>>>(n, k, M.p, prow.p, fcol.p);
+    ctx->launches += 4;
+  }
+  launched(ctx);
+  inv_rows.alloc((size_t)std::max<int64_t>(1, A->n_rows) * n);
+  if (A->n_rows) {
+    gj_extract_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)A->n_rows), 256, 0, ctx->stream>>>(n, row_off, A->n_rows,
+                                                                                                     M.p, inv_rows.p);
+    launched(ctx);
+  }
+  GSB_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+void dense_apply(gsb_ctx_t ctx, const DevBuf<double> &inv_rows, int64_t n_global, int64_t row_off, int64_t n_own,
+                 const gsb_vec_s &b, gsb_vec_s &x, DevBuf<double> &bfull) {
+  const double *bp = b.d;
+  if (ctx->nranks > 1) {
+    // gather the coarse rhs on every rank: zero-padded sum-allreduce (exact)
+    GSB_CUDA(cudaMemsetAsync(bfull.p, 0, sizeof(double) * n_global, ctx->stream));
+    if (n_own) GSB_CUDA(cudaMemcpyAsync(bfull.p + row_off, b.d, sizeof(double) * n_own, cudaMemcpyDeviceToDevice, ctx->stream));
+    GSB_NCCL(ncclAllReduce(bfull.p, bfull.p, n_global, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+    bp = bfull.p;
+  }
+  if (n_own == 0) return;
+  const int64_t warps = n_own;
+  const unsigned grid = (unsigned)((warps * 32 + 255) / 256);
+  dense_gemv_kernel<256><<<grid, 256, 0, ctx->stream>>>(n_own, n_global, inv_rows.p, bp, x.d);
+  launched(ctx);
+}
+
+}  // namespace gsb
+
+// ------------------------------------------------------------------------------------------ C ABI
+#define API_BEGIN try {
+#define API_END(ctx)                               \
+  }                                                \
+  catch (const gsb::Error &e) {                    \
+    gsb::set_error((ctx), e.msg);                  \
+    return e.code;                                 \
+  }                                                \
+  catch (const std::exception &e) {                \
+    gsb::set_error((ctx), e.what());               \
+    return GSB_EINVAL;                             \
+  }                                                \
+  return GSB_OK;
+
+namespace gsb {
+int set_error(gsb_ctx_t ctx, const std::string &msg);
+const std::string &last_error();
+}  // namespace gsb
+
+extern "C" {
+
+int gsb_version(void) { return 100; }
+
+const char *gsb_last_error(gsb_ctx_t ctx) {
+  (void)ctx;
+  return gsb::last_error().c_str();
+}
+
+int gsb_nccl_unique_id(void *out) {
+  API_BEGIN
+  static_assert(sizeof(ncclUniqueId) == GSB_NCCL_ID_BYTES, "ncclUniqueId size");
+  ncclUniqueId id;
+  GSB_NCCL(ncclGetUniqueId(&id));
+  std::memcpy(out, &id, sizeof(id));
+  API_END(nullptr)
+}
+
+int gsb_init(int device, int nranks, int rank, const void *nccl_id, gsb_ctx_t *out) {
+  API_BEGIN
+  GSB_CHECK(out != nullptr && nranks >= 1 && rank >= 0 && rank < nranks, "gsb_init: bad arguments");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    fail(GSB_ECUDA, "gsb_init: no CUDA device available (libgsb200 has no CPU fallback)");
+  GSB_CUDA(cudaSetDevice(device));
+  std::unique_ptr<gsb_ctx_s> ctx(new gsb_ctx_s());
+  ctx->device = device; ctx->nranks = nranks; ctx->rank = rank;
+  cudaDeviceProp prop;
+  GSB_CUDA(cudaGetDeviceProperties(&prop, device));
+  ctx->num_sms = prop.multiProcessorCount;
+  GSB_CHECK(prop.major >= 10, "gsb_init: libgsb200 is built for sm_100a (Blackwell) only");
+  GSB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  GSB_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+  GSB_CUDA(cudaEventCreate(&ctx->t0));
+  GSB_CUDA(cudaEventCreate(&ctx->t1));
+  GSB_CUDA(cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming));
+  GSB_CUDA(cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming));
+  ctx->scal.alloc(65536);
+  GSB_CUDA(cudaMemset(ctx->scal.p, 0, sizeof(double) * ctx->scal.n));
+  ctx->partials.alloc(PARTIALS_CAP);
+  ctx->ticket.alloc(4);
+  GSB_CUDA(cudaMemset(ctx->ticket.p, 0, sizeof(unsigned int) * 4));
+  GSB_CUDA(cudaMallocHost(&ctx->h_scal, sizeof(double) * 256));
+  if (nranks > 1) {
+    GSB_CHECK(nccl_id != nullptr, "gsb_init: nccl id required for nranks > 1");
+    ncclUniqueId id;
+    std::memcpy(&id, nccl_id, sizeof(id));
+    GSB_NCCL(ncclCommInitRank(&ctx->comm, nranks, id, rank));
+  }
+  *out = ctx.release();
+  API_END(nullptr)
+}
+
+int gsb_finalize(gsb_ctx_t ctx) {
+  API_BEGIN
+  if (!ctx) return GSB_OK;
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm) ncclCommDestroy(ctx->comm);
+  if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
+  cudaEventDestroy(ctx->t0); cudaEventDestroy(ctx->t1); cudaEventDestroy(ctx->ev_a); cudaEventDestroy(ctx->ev_b);
+  cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->comm_stream);
+  delete ctx;
+  API_END(nullptr)
+}
+
+int gsb_synchronize(gsb_ctx_t ctx) {
+  API_BEGIN
+  GSB_CUDA(cudaStreamSynchronize(ctx->stream));
+  API_END(ctx)
+}
+
+int gsb_timer_start(gsb_ctx_t ctx) {
+  API_BEGIN
+  GSB_CUDA(cudaEventRecord(ctx->t0, ctx->stream));
+  API_END(ctx)
+}
+
+int gsb_timer_stop(gsb_ctx_t ctx, float *ms) {
+  API_BEGIN
+  GSB_CUDA(cudaEventRecord(ctx->t1, ctx->stream));
+  GSB_CUDA(cudaEventSynchronize(ctx->t1));
+  GSB_CUDA(cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
+  API_END(ctx)
+}
+
+int gsb_launch_count(gsb_ctx_t ctx, int64_t *out) {
+  *out = ctx->launches;
+  return GSB_OK;
+}
+
+int gsb_set_option(gsb_ctx_t ctx, const char *key, const char *value) {
+  API_BEGIN
+  ctx->opts[key] = value;
+  API_END(ctx)
+}
+
+// ---------------------------------------------------------------- plan
+int gsb_plan_create(gsb_ctx_t ctx, int64_t n_own, int64_t n_ghost, int n_nbr_snd, const int32_t *nbr_snd,
+                    const int64_t *snd_ptrs, const int64_t *snd_local_ids, int n_nbr_rcv, const int32_t *nbr_rcv,
+                    const int64_t *rcv_ptrs, const int64_t *rcv_local_ids, int index_base, gsb_plan_t *out) {
+  API_BEGIN
+  std::unique_ptr<gsb_plan_s> p(new gsb_plan_s());
+  p->ctx = ctx; p->n_own = n_own; p->n_ghost = n_ghost;
+  p->nbr_snd.assign(nbr_snd, nbr_snd + n_nbr_snd);
+  p->nbr_rcv.assign(nbr_rcv, nbr_rcv + n_nbr_rcv);
+  p->snd_ptrs.resize((size_t)n_nbr_snd + 1);
+  p->rcv_ptrs.resize((size_t)n_nbr_rcv + 1);
+  for (int k = 0; k <= n_nbr_snd; ++k) p->snd_ptrs[(size_t)k] = snd_ptrs[k] - snd_ptrs[0];
+  for (int k = 0; k <= n_nbr_rcv; ++k) p->rcv_ptrs[(size_t)k] = rcv_ptrs[k] - rcv_ptrs[0];
+  for (int k = 0; k < n_nbr_snd; ++k) { p->nbr_snd[(size_t)k] -= 0; }
+  const int64_t nsnd = p->snd_ptrs.back(), nrcv = p->rcv_ptrs.back();
+  std::vector<int> s((size_t)nsnd), r((size_t)nrcv);
+  for (int64_t i = 0; i < nsnd; ++i) {
+    int64_t id = snd_local_ids[i] - index_base;
+    GSB_CHECK(id >= 0 && id < n_own, "plan: send id is not an own entry");
+    s[(size_t)i] = (int)id;
+  }
+  for (int64_t i = 0; i < nrcv; ++i) {
+    int64_t id = rcv_local_ids[i] - index_base;
+    GSB_CHECK(id >= n_own && id < n_own + n_ghost, "plan: receive id is not a ghost entry");
+    r[(size_t)i] = (int)id;
+  }
+  p->snd_ids.alloc(std::max<size_t>(1, s.size()));
+  p->rcv_ids.alloc(std::max<size_t>(1, r.size()));
+  p->snd_buf.alloc(std::max<size_t>(1, s.size()));
+  p->rcv_buf.alloc(std::max<size_t>(1, r.size()));
+  if (nsnd) GSB_CUDA(cudaMemcpy(p->snd_ids.p, s.data(), sizeof(int) * s.size(), cudaMemcpyHostToDevice));
+  if (nrcv) GSB_CUDA(cudaMemcpy(p->rcv_ids.p, r.data(), sizeof(int) * r.size(), cudaMemcpyHostToDevice));
+  *out = p.release();
+  API_END(ctx)
+}
+
+int gsb_plan_destroy(gsb_plan_t plan) {
+  delete plan;
+  return GSB_OK;
+}
+
+// ---------------------------------------------------------------- matrix
+static int64_t rd_idx(const void *p, int bytes, int64_t i) {
+  return bytes == 8 ? ((const int64_t *)p)[i] : (int64_t)((const int32_t *)p)[i];
+}
+
+static void finish_matrix(gsb_mat_s *A, const std::vector<int> &rowptr, const std::vector<int> &col,
+                          const std::vector<double> &val) {
+  gsb_ctx_t ctx = A->ctx;
+  A->nnz = (int64_t)col.size();
+  A->nnz_padded = (A->nnz + 3) & ~(int64_t)3;
+  if (A->nnz_padded == 0) A->nnz_padded = 4;
+  A->rowptr.alloc(rowptr.size());
+  A->col.alloc((size_t)A->nnz_padded);
+  A->val.alloc((size_t)A->nnz_padded);
+  GSB_CUDA(cudaMemset(A->col.p, 0, sizeof(int) * A->nnz_padded));
+  GSB_CUDA(cudaMemset(A->val.p, 0, sizeof(double) * A->nnz_padded));
+  GSB_CUDA(cudaMemcpy(A->rowptr.p, rowptr.data(), sizeof(int) * rowptr.size(), cudaMemcpyHostToDevice));
+  if (A->nnz) {
+    GSB_CUDA(cudaMemcpy(A->col.p, col.data(), sizeof(int) * col.size(), cudaMemcpyHostToDevice));
+    GSB_CUDA(cudaMemcpy(A->val.p, val.data(), sizeof(double) * val.size(), cudaMemcpyHostToDevice));
+  }
+  int mx = 0;
+  for (int64_t i = 0; i < A->n_rows; ++i) mx = std::max(mx, rowptr[(size_t)i + 1] - rowptr[(size_t)i]);
+  A->max_row_nnz = mx;
+  const double avg = A->n_rows ? (double)A->nnz / (double)A->n_rows : 0.0;
+  A->G = avg <= 48.0 ? 1 : (avg <= 160.0 ? 4 : 16);
+  A->stream_ok = mx <= ST_SPAN_MAX && A->n_rows > 0;
+  // persistent-CTA row partition balanced by nnz
+  const int rows_per_step = ST_THREADS / A->G;
+  int n_ctas = (int)std::min<int64_t>(ctx->num_sms, std::max<int64_t>(1, (A->n_rows + rows_per_step - 1) / rows_per_step));
+  std::vector<int> cta_rows((size_t)n_ctas + 1, 0);
+  for (int b = 1; b < n_ctas; ++b) {
+    const int64_t target = (int64_t)((double)A->nnz * b / n_ctas);
+    auto it = std::lower_bound(rowptr.begin(), rowptr.end(), (int)target);
+    int r = (int)(it - rowptr.begin());
+    r = std::min<int>(r, (int)A->n_rows);
+    cta_rows[(size_t)b] = std::max(r, cta_rows[(size_t)b - 1]);
+  }
+  cta_rows[(size_t)n_ctas] = (int)A->n_rows;
+  A->n_ctas = n_ctas;
+  A->cta_rows.alloc(cta_rows.size());
+  GSB_CUDA(cudaMemcpy(A->cta_rows.p, cta_rows.data(), sizeof(int) * cta_rows.size(), cudaMemcpyHostToDevice));
+}
+
+int gsb_mat_create(gsb_ctx_t ctx, int64_t n_rows, int64_t n_own_cols, int64_t n_ghost_cols, int fmt, int index_base,
+                   int index_bytes, const void *ptr, const void *idx, const double *vals, gsb_plan_t plan,
+                   gsb_mat_t *out) {
+  API_BEGIN
+  GSB_CHECK(index_bytes == 4 || index_bytes == 8, "mat: index_bytes must be 4 or 8");
+  GSB_CHECK(fmt == GSB_FMT_CSR || fmt == GSB_FMT_CSC, "mat: unknown format");
+  GSB_CHECK(n_ghost_cols == 0 || ctx->nranks == 1 || plan != nullptr, "mat: ghost columns need an exchange plan");
+  const int64_t n_cols = n_own_cols + n_ghost_cols;
+  GSB_CHECK(n_rows < INT32_MAX && n_cols < INT32_MAX, "mat: local dimensions exceed int32");
+  std::unique_ptr<gsb_mat_s> A(new gsb_mat_s());
+  A->ctx = ctx; A->n_rows = n_rows; A->n_own_cols = n_own_cols; A->n_ghost_cols = n_ghost_cols; A->plan = plan;
+  const int64_t nptr = (fmt == GSB_FMT_CSR ? n_rows : n_cols);
+  const int64_t nnz = rd_idx(ptr, index_bytes, nptr) - rd_idx(ptr, index_bytes, 0);
+  GSB_CHECK(nnz >= 0 && nnz < INT32_MAX - 8, "mat: local nnz exceeds int32");
+  const int64_t p0 = rd_idx(ptr, index_bytes, 0);
+  std::vector<int> rowptr((size_t)n_rows + 1, 0), col((size_t)nnz);
+  std::vector<double> val((size_t)nnz);
+  if (fmt == GSB_FMT_CSR) {
+    bool sorted = true;
+    for (int64_t i = 0; i <= n_rows; ++i) rowptr[(size_t)i] = (int)(rd_idx(ptr, index_bytes, i) - p0);
+    for (int64_t e = 0; e < nnz; ++e) {
+      int64_t c = rd_idx(idx, index_bytes, e) - index_base;
+      GSB_CHECK(c >= 0 && c < n_cols, "mat: column index out of range");
+      col[(size_t)e] = (int)c;
+      val[(size_t)e] = vals[e];
+    }
+    for (int64_t i = 0; i < n_rows && sorted; ++i)
+      for (int e = rowptr[(size_t)i] + 1; e < rowptr[(size_t)i + 1]; ++e)
+        if (col[(size_t)e] <= col[(size_t)e - 1]) { sorted = false; break; }
+    if (!sorted) {
+      A->perm.resize((size_t)nnz);
+      std::iota(A->perm.begin(), A->perm.end(), (int64_t)0);
+      for (int64_t i = 0; i < n_rows; ++i)
+        std::sort(A->perm.begin() + rowptr[(size_t)i], A->perm.begin() + rowptr[(size_t)i + 1],
+                  [&](int64_t a, int64_t b) { return col[(size_t)a] < col[(size_t)b]; });
+      std::vector<int> c2((size_t)nnz);
+      std::vector<double> v2((size_t)nnz);
+      for (int64_t e = 0; e < nnz; ++e) { c2[(size_t)e] = col[(size_t)A->perm[(size_t)e]]; v2[(size_t)e] = val[(size_t)A->perm[(size_t)e]]; }
+      col.swap(c2); val.swap(v2);
+    }
+  } else {  // CSC -> CSR; visiting columns in ascending order leaves every row sorted
+    A->perm.resize((size_t)nnz);
+    for (int64_t e = 0; e < nnz; ++e) {
+      int64_t r = rd_idx(idx, index_bytes, e) - index_base;
+      GSB_CHECK(r >= 0 && r < n_rows, "mat: row index out of range");
+      rowptr[(size_t)r + 1]++;
+    }
+    for (int64_t i = 0; i < n_rows; ++i) rowptr[(size_t)i + 1] += rowptr[(size_t)i];
+    std::vector<int> fillp(rowptr.begin(), rowptr.end() - 1);
+    for (int64_t j = 0; j < n_cols; ++j) {
+      const int64_t a = rd_idx(ptr, index_bytes, j) - p0, b = rd_idx(ptr, index_bytes, j + 1) - p0;
+      for (int64_t e = a; e < b; ++e) {
+        const int64_t r = rd_idx(idx, index_bytes, e) - index_base;
+        const int pos = fillp[(size_t)r]++;
+        col[(size_t)pos] = (int)j;
+        val[(size_t)pos] = vals[e];
+        A->perm[(size_t)pos] = e;
+      }
+    }
+  }
+  finish_matrix(A.get(), rowptr, col, val);
+  *out = A.release();
+  API_END(ctx)
+}
+
+int gsb_mat_update_values(gsb_mat_t A, const double *vals) {
+  API_BEGIN
+  GSB_CHECK(A->nb == 0, "update_values: block matrix");
+  if (A->perm.empty()) {
+    GSB_CUDA(cudaMemcpy(A->val.p, vals, sizeof(double) * A->nnz, cudaMemcpyHostToDevice));
+  } else {
+    std::vector<double> v((size_t)A->nnz);
+    for (int64_t e = 0; e < A->nnz; ++e) v[(size_t)e] = vals[A->perm[(size_t)e]];
+    GSB_CUDA(cudaMemcpy(A->val.p, v.data(), sizeof(double) * A->nnz, cudaMemcpyHostToDevice));
+  }
+  API_END(A->ctx)
+}
+
+int gsb_mat_info(gsb_mat_t A, int64_t *n_rows, int64_t *n_own_cols, int64_t *n_ghost_cols, int64_t *nnz) {
+  if (n_rows) *n_rows = A->n_rows;
+  if (n_own_cols) *n_own_cols = A->n_own_cols;
+  if (n_ghost_cols) *n_ghost_cols = A->n_ghost_cols;
+  if (nnz) *nnz = A->nnz;
+  return GSB_OK;
+}
+
+int gsb_mat_destroy(gsb_mat_t A) {
+  delete A;
+  return GSB_OK;
+}
+
+int gsb_block_mat_create(gsb_ctx_t ctx, int nb, const gsb_mat_t *blocks, gsb_mat_t *out) {
+  API_BEGIN
+  GSB_CHECK(nb >= 1, "block matrix: nb < 1");
+  std::unique_ptr<gsb_mat_s> A(new gsb_mat_s());
+  A->ctx = ctx; A->nb = nb;
+  A->blocks.assign(blocks, blocks + (size_t)nb * nb);
+  std::vector<int64_t> rs((size_t)nb, -1), cs((size_t)nb, -1);
+  for (int i = 0; i < nb; ++i)
+    for (int j = 0; j < nb; ++j) {
+      gsb_mat_t B = A->blocks[(size_t)i * nb + j];
+      if (!B) continue;
+      GSB_CHECK(B->n_ghost_cols == 0, "block matrix: distributed blocks not supported");
+      GSB_CHECK(rs[(size_t)i] < 0 || rs[(size_t)i] == B->n_rows, "block matrix: inconsistent block rows");
+      GSB_CHECK(cs[(size_t)j] < 0 || cs[(size_t)j] == B->n_own_cols, "block matrix: inconsistent block cols");
+      rs[(size_t)i] = B->n_rows; cs[(size_t)j] = B->n_own_cols;
+      A->nnz += B->nnz;
+    }
+  A->row_off.assign((size_t)nb + 1, 0); A->col_off.assign((size_t)nb + 1, 0);
+  for (int i = 0; i < nb; ++i) {
+    GSB_CHECK(rs[(size_t)i] >= 0 && cs[(size_t)i] >= 0, "block matrix: empty block row/column");
+    A->row_off[(size_t)i + 1] = A->row_off[(size_t)i] + rs[(size_t)i];
+    A->col_off[(size_t)i + 1] = A->col_off[(size_t)i] + cs[(size_t)i];
+  }
+  A->n_rows = A->row_off.back(); A->n_own_cols = A->col_off.back();
+  *out = A.release();
+  API_END(ctx)
+}
+
+// ---------------------------------------------------------------- vectors
+int gsb_vec_create(gsb_ctx_t ctx, int64_t n_own, int64_t n_ghost, gsb_vec_t *out) {
+  API_BEGIN
+  GSB_CHECK(n_own >= 0 && n_ghost >= 0, "vec: negative size");
+  std::unique_ptr<gsb_vec_s> v(new gsb_vec_s());
+  v->ctx = ctx; v->n_own = n_own; v->n_ghost = n_ghost;
+  GSB_CUDA(cudaMalloc(&v->d, sizeof(double) * std::max<int64_t>(1, n_own + n_ghost)));
+  GSB_CUDA(cudaMemsetAsync(v->d, 0, sizeof(double) * std::max<int64_t>(1, n_own + n_ghost), ctx->stream));
+  *out = v.release();
+  API_END(ctx)
+}
+int gsb_vec_create_domain(gsb_mat_t A, gsb_vec_t *out) { return gsb_vec_create(A->ctx, A->n_own_cols, A->n_ghost_cols, out); }
+int gsb_vec_create_range(gsb_mat_t A, gsb_vec_t *out) { return gsb_vec_create(A->ctx, A->n_rows, 0, out); }
+int gsb_vec_destroy(gsb_vec_t v) {
+  delete v;
+  return GSB_OK;
+}
+int gsb_vec_size(gsb_vec_t v, int64_t *n_own, int64_t *n_ghost) {
+  if (n_own) *n_own = v->n_own;
+  if (n_ghost) *n_ghost = v->n_ghost;
+  return GSB_OK;
+}
+int gsb_vec_set(gsb_vec_t v, const double *host, int64_t n) {
+  API_BEGIN
+  GSB_CHECK(n == v->n_own, "vec_set: length != own size");
+  if (n) GSB_CUDA(cudaMemcpyAsync(v->d, host, sizeof(double) * n, cudaMemcpyHostToDevice, v->ctx->stream));
+  GSB_CUDA(cudaStreamSynchronize(v->ctx->stream));
+  API_END(v->ctx)
+}
+int gsb_vec_get(gsb_vec_t v, double *host, int64_t n) {
+  API_BEGIN
+  GSB_CHECK(n == v->n_own, "vec_get: length != own size");
+  if (n) GSB_CUDA(cudaMemcpyAsync(host, v->d, sizeof(double) * n, cudaMemcpyDeviceToHost, v->ctx->stream));
+  GSB_CUDA(cudaStreamSynchronize(v->ctx->stream));
+  API_END(v->ctx)
+}
+int gsb_vec_get_local(gsb_vec_t v, double *host, int64_t n) {
+  API_BEGIN
+  GSB_CHECK(n == v->n_local(), "vec_get_local: length != local size");
+  if (n) GSB_CUDA(cudaMemcpyAsync(host, v->d, sizeof(double) * n, cudaMemcpyDeviceToHost, v->ctx->stream));
+  GSB_CUDA(cudaStreamSynchronize(v->ctx->stream));
+  API_END(v->ctx)
+}
+int gsb_vec_fill(gsb_vec_t v, double value) {
+  API_BEGIN
+  gsb::vec_fill(*v, value);
+  API_END(v->ctx)
+}
+int gsb_vec_copy(gsb_vec_t dst, gsb_vec_t src) {
+  API_BEGIN
+  gsb::vec_copy(*dst, *src);
+  API_END(dst->ctx)
+}
+int gsb_vec_consistent(gsb_vec_t v, gsb_plan_t plan) {
+  API_BEGIN
+  gsb::consistent(*v, plan);
+  GSB_CUDA(cudaStreamSynchronize(v->ctx->stream));
+  API_END(v->ctx)
+}
+
+// ---------------------------------------------------------------- primitives
+int gsb_spmv(gsb_mat_t A, gsb_vec_t x, gsb_vec_t y, double alpha, double beta) {
+  API_BEGIN
+  gsb::spmv(A, *x, *y, alpha, beta);
+  API_END(A->ctx)
+}
+int gsb_dot(gsb_vec_t a, gsb_vec_t b, double *out) {
+  API_BEGIN
+  gsb::dot(*a, *b, 0);
+  *out = a->ctx->read_scalar(0);
+  API_END(a->ctx)
+}
+int gsb_norm2(gsb_vec_t a, double *out) {
+  API_BEGIN
+  gsb::dot(*a, *a, 0);
+  *out = std::sqrt(a->ctx->read_scalar(0));
+  API_END(a->ctx)
+}
+int gsb_axpby(gsb_vec_t z, double alpha, gsb_vec_t x, double beta, gsb_vec_t y) {
+  API_BEGIN
+  gsb::ew_axpby(*z, gsb::imm(alpha), *x, gsb::imm(beta), y);
+  API_END(z->ctx)
+}
+
+}  // extern "C"

@@ -1,0 +1,185 @@
+// gsb_internal.h -- host-side objects behind the opaque handles of include/gsb200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include <stdint.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/gsb200.h"
+#include "types.h"
+
+namespace gsb {
+
+struct Error {
+  int code;
+  std::string msg;
+};
+[[noreturn]] void fail(int code, const std::string &msg);
+
+#define GSB_CUDA(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t e_ = (expr);                                                                             \
+    if (e_ != cudaSuccess)                                                                               \
+      ::gsb::fail(GSB_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + \
+                                 std::to_string(__LINE__) + ")");                                        \
+  } while (0)
+#define GSB_NCCL(expr)                                                                                    \
+  do {                                                                                                    \
+    ncclResult_t e_ = (expr);                                                                             \
+    if (e_ != ncclSuccess)                                                                                \
+      ::gsb::fail(GSB_ENCCL, std::string(#expr) + ": " + ncclGetErrorString(e_) + " (" + __FILE__ + ":" + \
+                                 std::to_string(__LINE__) + ")");                                         \
+  } while (0)
+#define GSB_CHECK(cond, msg)                          \
+  do {                                                \
+    if (!(cond)) ::gsb::fail(GSB_EINVAL, (msg));      \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  explicit DevBuf(size_t n_) { alloc(n_); }
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf &operator=(DevBuf &&o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void alloc(size_t n_) {
+    release();
+    n = n_;
+    if (n) GSB_CUDA(cudaMalloc(&p, n * sizeof(T)));
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+}  // namespace gsb
+
+struct gsb_ctx_s {
+  int device = 0, nranks = 1, rank = 0, num_sms = 148;
+  cudaStream_t stream = nullptr;       // compute stream
+  cudaStream_t comm_stream = nullptr;  // halo stream
+  ncclComm_t comm = nullptr;
+  cudaEvent_t t0 = nullptr, t1 = nullptr, ev_a = nullptr, ev_b = nullptr;
+  int64_t launches = 0;
+  // device scalars + reduction scratch
+  gsb::DevBuf<double> scal;
+  int next_slot = 8;  // slots 0..7: scratch for the C-ABI dot/norm calls
+  gsb::DevBuf<double> partials;
+  gsb::DevBuf<unsigned int> ticket;
+  double *h_scal = nullptr;  // pinned host mirror for read-backs
+  std::map<std::string, std::string> opts;
+  std::string err;
+  int alloc_slots(int n);
+  double read_scalar(int slot);                 // blocking
+  void read_scalars(int slot, int n, double *out);
+  void allreduce_slot(int slot, int n = 1);     // in-place NCCL allreduce when nranks > 1
+  gsb::ReduceOut reduce_out(int slot);
+  std::string opt(const std::string &k, const std::string &dflt) const {
+    auto it = opts.find(k);
+    return it == opts.end() ? dflt : it->second;
+  }
+};
+
+struct gsb_plan_s {
+  gsb_ctx_t ctx;
+  int64_t n_own = 0, n_ghost = 0;
+  std::vector<int> nbr_snd, nbr_rcv;
+  std::vector<int64_t> snd_ptrs, rcv_ptrs;  // per-neighbour offsets into the id lists
+  gsb::DevBuf<int> snd_ids, rcv_ids;        // 0-based local ids
+  gsb::DevBuf<double> snd_buf, rcv_buf;
+  bool rcv_contiguous = false;  // ghosts of each neighbour form one ascending run -> no unpack
+};
+
+struct gsb_vec_s {
+  gsb_ctx_t ctx;
+  int64_t n_own = 0, n_ghost = 0;
+  double *d = nullptr;
+  bool owns = true;
+  int64_t n_local() const { return n_own + n_ghost; }
+  ~gsb_vec_s() {
+    if (owns && d) cudaFree(d);
+  }
+};
+
+struct gsb_mat_s {
+  gsb_ctx_t ctx;
+  int64_t n_rows = 0, n_own_cols = 0, n_ghost_cols = 0, nnz = 0, nnz_padded = 0;
+  gsb_plan_t plan = nullptr;
+  gsb::DevBuf<int> rowptr, col;
+  gsb::DevBuf<double> val;
+  // upload permutation: position in the caller's value array of each CSR entry (for update_values)
+  std::vector<int64_t> perm;  // empty == identity
+  int max_row_nnz = 0;
+  int G = 1;  // lanes per row
+  // streaming kernel partition
+  bool stream_ok = false;
+  int n_ctas = 0;
+  gsb::DevBuf<int> cta_rows;
+  // block matrix (acts on concatenated vectors)
+  int nb = 0;
+  std::vector<gsb_mat_t> blocks;  // row-major nb*nb, may contain nullptr
+  std::vector<int64_t> row_off, col_off;
+};
+
+namespace gsb {
+
+struct Log {
+  int maxiter = 1000;
+  double atol = 1e-12, rtol = 1e-6;
+  int num_iters = 0;
+  int flag = 0;
+  std::vector<double> residuals;
+  void configure(int maxiter_, double atol_, double rtol_) {
+    maxiter = maxiter_; atol = atol_; rtol = rtol_;
+    residuals.assign((size_t)maxiter + 1, 0.0);
+  }
+  bool finished(int niter, double e_a, double e_r) const {  // SolverTolerances.jl:117-128
+    return (niter >= maxiter) || (e_r < rtol) || (e_a < atol);
+  }
+  bool init(double r0) {  // ConvergenceLogs.jl:101-112
+    num_iters = 0;
+    std::fill(residuals.begin(), residuals.end(), 0.0);
+    residuals[0] = r0;
+    return finished(0, r0, 1.0);
+  }
+  bool update(double r) {  // ConvergenceLogs.jl:119-129
+    num_iters += 1;
+    residuals[(size_t)num_iters] = r;
+    return finished(num_iters, r, r / residuals[0]);
+  }
+  int finalize(double r) {  // ConvergenceLogs.jl:136-150 ; SolverTolerances.jl:97-110
+    const double e_r = r / residuals[0];
+    if (e_r < rtol) flag = GSB_CONVERGED_RTOL;
+    else if (r < atol) flag = GSB_CONVERGED_ATOL;
+    else if (num_iters >= maxiter) flag = GSB_DIVERGED_MAXITER;
+    else flag = GSB_DIVERGED_BREAKDOWN;
+    return flag;
+  }
+};
+
+}  // namespace gsb
+
+struct gsb_solver_s {
+  gsb_ctx_t ctx = nullptr;
+  gsb::Log log;
+  bool has_log = false;
+  virtual ~gsb_solver_s() {}
+  virtual void solve(gsb_vec_s &x, gsb_vec_s &b) = 0;  // solve!(x,ns,b)
+  virtual void update(gsb_mat_t A) { (void)A; }       // numerical_setup!(ns,A)
+  virtual const char *name() const = 0;
+  virtual gsb_mat_t matrix() { return nullptr; }       // the system matrix, when the solver has one
+  std::unique_ptr<gsb_vec_s> host_x, host_b;           // staging for gsb_solve_host
+};

@@ -1,0 +1,482 @@
+// kernels.cuh -- hand-written sm_100a kernels of the gsb200 solve phase.
+//
+// Every kernel here is HBM-bandwidth bound: the design rules are perfectly
+// streamed matrix traffic (TMA bulk copies of the CSR value / column arrays into a shared-memory
+// ring, persistent CTAs), coalesced gathers of the input vector (one lane per row => the k-th
+// neighbours of consecutive rows are consecutive in memory on mesh-ordered matrices), fusion of
+// every elementwise epilogue into the row kernel, and deterministic two-stage reductions.
+//
+// Rounding contract (DESIGN.md "parity"): a row sum is accumulated in ascending column order,
+// product rounded before the add (no FMA contraction) -- the sequence Julia's SparseArrays /
+// SparseMatricesCSR mul! produce (oracle/csr_kernels.c) -- so with one lane per row the SpMV,
+// smoother and transfer kernels are bit-identical to the CPU oracle.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "types.h"
+
+namespace gsb {
+
+// ------------------------------------------------------------------------------------------
+// device scalars: Krylov coefficients live in a small device array; kernels take references
+// to them so that the host never has to read gamma/alpha/beta back (one sync per iteration,
+// for the stopping test only).
+__device__ __forceinline__ double load_scalar(const ScalarRef &r, const double *__restrict__ scal) {
+  double s = r.v;
+  if (r.num >= 0) {
+    s = scal[r.num];
+    if (r.sub >= 0) s = __dsub_rn(s, scal[r.sub]);
+    if (r.den >= 0) s = __ddiv_rn(s, scal[r.den]);
+  }
+  return r.neg ? -s : s;
+}
+
+// ------------------------------------------------------------------------------------------
+// deterministic block reduction + "last block finalises" grid reduction
+template <int THREADS>
+__device__ __forceinline__ double block_reduce_sum(double v, double *smem /* THREADS/32 doubles */) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) smem[w] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (w == 0) {
+    t = (l < THREADS / 32) ? smem[l] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  }
+  __syncthreads();
+  return t;  // valid in warp 0 (all lanes)
+}
+
+// every block calls this with its partial(s); the last block to arrive sums all partials in a
+// fixed order and stores the totals => bitwise reproducible for a fixed grid size.
+template <int THREADS, int NRED>
+__device__ __forceinline__ void grid_reduce_finish(double (&v)[NRED], const ReduceOut &ro, double *smem) {
+  __shared__ bool is_last;
+#pragma unroll
+  for (int k = 0; k < NRED; ++k) {
+    double t = block_reduce_sum<THREADS>(v[k], smem);
+    if (threadIdx.x == 0) ro.partials[(size_t)k * gridDim.x + blockIdx.x] = t;
+  }
+  __threadfence();
+  if (threadIdx.x == 0) {
+    unsigned int prev = atomicAdd(ro.ticket, 1u);
+    is_last = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+#pragma unroll
+    for (int k = 0; k < NRED; ++k) {
+      double t = 0.0;
+      const volatile double *p = ro.partials + (size_t)k * gridDim.x;
+      for (unsigned int i = threadIdx.x; i < gridDim.x; i += THREADS) t += p[i];
+      t = block_reduce_sum<THREADS>(t, smem);
+      if (threadIdx.x == 0) ro.scal[ro.slot[k]] = t;
+    }
+    if (threadIdx.x == 0) *ro.ticket = 0u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// row epilogues shared by the CSR kernels
+template <int MODE>
+__device__ __forceinline__ double row_init(const RowArgs &a, int64_t row) {
+  if (MODE == ROW_SPMV) {
+    if (a.beta == 0.0) return 0.0;
+    if (a.beta == 1.0) return a.y[row];
+    return __dmul_rn(a.beta, a.y[row]);
+  }
+  return 0.0;
+}
+
+template <int MODE>
+__device__ __forceinline__ void row_epilogue(const RowArgs &a, int64_t row, double s, double &acc) {
+  if (MODE == ROW_SPMV) {
+    a.y[row] = s;
+  } else if (MODE == ROW_RESID) {
+    a.out[row] = __dsub_rn(a.b[row], s);
+  } else if (MODE == ROW_SWEEP) {
+    const double r = __dsub_rn(a.b[row], s);
+    a.out[row] = r;
+    const double d = __dmul_rn(a.omega, __dmul_rn(a.invd[row], r));
+    a.dxout[row] = d;
+    a.xacc[row] = __dadd_rn(a.xacc[row], d);
+  } else if (MODE == ROW_SPMV_DOT) {
+    a.y[row] = s;
+    acc = __dadd_rn(acc, __dmul_rn(a.dotv[row], s));
+  } else if (MODE == ROW_SPMV_ADD) {
+    a.y[row] = s;
+    a.xacc[row] = __dadd_rn(a.xacc[row], s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// generic CSR kernel: G lanes per row, direct global loads.  Used for small levels (launch /
+// latency bound) and for matrices whose rows do not fit the streaming kernel's ring.
+template <int G, int MODE, int THREADS>
+__global__ void __launch_bounds__(THREADS) csr_vector_kernel(int64_t nrows, const int *__restrict__ rowptr,
+                                                            const int *__restrict__ col,
+                                                            const double *__restrict__ val, RowArgs a) {
+  __shared__ double red_smem[THREADS / 32];
+  const int64_t row = ((int64_t)blockIdx.x * THREADS + threadIdx.x) / G;
+  const int lane = threadIdx.x % G;
+  double acc = 0.0;
+  double s = 0.0;
+  const bool valid = row < nrows;
+  if (valid) {
+    const int e0 = rowptr[row], e1 = rowptr[row + 1];
+    const double al = a.alpha;
+    if (lane == 0) s = row_init<MODE>(a, row);
+    for (int e = e0 + lane; e < e1; e += G) {
+      double xv = __ldg(a.x + col[e]);
+      if (MODE == ROW_SPMV) xv = __dmul_rn(xv, al);
+      s = __dadd_rn(s, __dmul_rn(val[e], xv));
+    }
+  }
+  if (G > 1) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) s = __dadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
+  }
+  if (valid && lane == 0) row_epilogue<MODE>(a, row, s, acc);
+  if (MODE == ROW_SPMV_DOT) {
+    double v[1] = {acc};
+    grid_reduce_finish<THREADS, 1>(v, a.red, red_smem);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + TMA 1-D bulk copy (cp.async.bulk, SASS: UBLKCP)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// streaming CSR kernel (the hot kernel): persistent CTAs, each owning a contiguous block of rows
+// (balanced by nnz at set-up time).  One elected thread streams the CTA's slice of val[] / col[]
+// through a shared-memory ring with TMA bulk copies (CHUNK non-zeros per copy, one mbarrier per
+// ring slot); the other threads never touch DRAM for matrix data.  THREADS/G rows are processed
+// per step, G lanes per row walking the row's segment of the ring; gathers of x go through L1/L2.
+//   ring bytes = RING*(8+4); in flight per SM ~ (RING - group span) * 12 B.
+template <int G, int MODE, int THREADS, int RING_LOG2, int CHUNK_LOG2>
+__global__ void __launch_bounds__(THREADS) csr_stream_kernel(StreamArgs m, RowArgs a) {
+  constexpr int RING = 1 << RING_LOG2;
+  constexpr int CHUNK = 1 << CHUNK_LOG2;
+  constexpr int NSLOT = RING / CHUNK;
+  constexpr int ROWS = THREADS / G;
+  constexpr int SPAN_MAX = RING / 2;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *sval = reinterpret_cast<double *>(smem_raw);
+  int *scol = reinterpret_cast<int *>(smem_raw + (size_t)RING * 8);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)RING * 12);
+  __shared__ double red_smem[THREADS / 32];
+
+  const int R0 = m.cta_rows[blockIdx.x], R1 = m.cta_rows[blockIdx.x + 1];
+  double acc = 0.0;
+  if (R0 < R1) {
+    const int E0 = m.rowptr[R0], E1 = m.rowptr[R1];
+    const int S0 = E0 & ~3;  // 16-byte aligned start of this CTA's stream
+    const int nchunks = (E1 - S0 + CHUNK - 1) >> CHUNK_LOG2;
+    if (threadIdx.x == 0) {
+      for (int s = 0; s < NSLOT; ++s) mbar_init(&full[s], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    int issued = 0;  // next chunk to issue (thread 0 only)
+    const int t_row = threadIdx.x / G, lane = threadIdx.x % G;
+    int g0 = R0;
+    // row pointers of the first group
+    int rp0 = 0, rp1 = 0;
+    {
+      const int r = g0 + t_row;
+      if (r < R1) { rp0 = m.rowptr[r]; rp1 = m.rowptr[r + 1]; }
+    }
+    __shared__ int s_gbase;
+    while (g0 < R1) {
+      if (threadIdx.x == 0) s_gbase = rp0;  // thread 0 holds the row pointer of row g0
+      // barrier #1: the previous group is fully consumed (its ring slots may be refilled) and
+      // the base of this group is published
+      __syncthreads();
+      const int gbase = s_gbase;
+      const bool in_rng = (g0 + t_row < R1);
+      // barrier #2: n = number of rows of this group (row-pointer prefix within SPAN_MAX)
+      const int n = __syncthreads_count(in_rng && lane == 0 && (rp1 - gbase) <= SPAN_MAX);
+      const int clo = (gbase - S0) >> CHUNK_LOG2;
+      if (threadIdx.x == 0) {
+        const int lim = min(nchunks, clo + NSLOT);
+        for (; issued < lim; ++issued) {
+          const int slot = issued & (NSLOT - 1);
+          const int64_t start = (int64_t)S0 + ((int64_t)issued << CHUNK_LOG2);
+          int64_t cnt = m.nnz_padded - start;
+          if (cnt > CHUNK) cnt = CHUNK;
+          mbar_expect_tx(&full[slot], (uint32_t)cnt * 12u);
+          tma_bulk_g2s(sval + (size_t)slot * CHUNK, m.val + start, (uint32_t)cnt * 8u, &full[slot]);
+          tma_bulk_g2s(scol + (size_t)slot * CHUNK, m.col + start, (uint32_t)cnt * 4u, &full[slot]);
+        }
+      }
+      const bool active = (t_row < n);
+      const int e0 = rp0, e1 = rp1;
+      const int64_t row = g0 + t_row;
+      // prefetch the next group's row pointers while this one is processed
+      {
+        const int r = g0 + n + t_row;
+        rp0 = 0; rp1 = 0;
+        if (r < R1) { rp0 = m.rowptr[r]; rp1 = m.rowptr[r + 1]; }
+      }
+      double s = 0.0;
+      if (active) {
+        if (e1 > e0) {
+          const int c0 = (e0 - S0) >> CHUNK_LOG2, c1 = (e1 - 1 - S0) >> CHUNK_LOG2;
+          for (int c = c0; c <= c1; ++c) mbar_wait(&full[c & (NSLOT - 1)], (uint32_t)((c / NSLOT) & 1));
+        }
+        if (lane == 0) s = row_init<MODE>(a, row);
+        const double al = a.alpha;
+#pragma unroll 4
+        for (int e = e0 + lane; e < e1; e += G) {
+          const int p = (e - S0) & (RING - 1);
+          const int c = scol[p];
+          const double v = sval[p];
+          double xv = __ldg(a.x + c);
+          if (MODE == ROW_SPMV) xv = __dmul_rn(xv, al);
+          s = __dadd_rn(s, __dmul_rn(v, xv));
+        }
+      }
+      if (G > 1) {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) s = __dadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
+      }
+      if (active && lane == 0) row_epilogue<MODE>(a, row, s, acc);
+      g0 += n;
+    }
+  }
+  if (MODE == ROW_SPMV_DOT) {
+    double v[1] = {acc};
+    grid_reduce_finish<THREADS, 1>(v, a.red, red_smem);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// BLAS-1: z = ((a*x + b*y) + c*w) / d   evaluated left to right, each product rounded before
+// the add (matches Julia's broadcast of `x .+ s .* y`, `x .- s .* y`, `(z .- a2.*w .- a3.*wo) ./ a1`).
+// a == 1 is exact (1*x == x), b*y with b = -s equals -(s*y) exactly.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) ew_kernel(EwArgs g) {
+  const double a = load_scalar(g.a, g.scal), b = load_scalar(g.b, g.scal), c = load_scalar(g.c, g.scal),
+               d = load_scalar(g.d, g.scal);
+  for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < g.n; i += (int64_t)gridDim.x * THREADS) {
+    double v;
+    if (g.mul_xy) {
+      v = __dmul_rn(g.x[i], g.y[i]);
+    } else {
+      v = __dmul_rn(a, g.x[i]);
+      if (g.has_y) v = __dadd_rn(v, __dmul_rn(b, g.y[i]));
+      if (g.has_w) v = __dadd_rn(v, __dmul_rn(c, g.w[i]));
+      if (g.has_d) v = __ddiv_rn(v, d);
+    }
+    g.z[i] = v;
+  }
+}
+
+// Jacobi-Richardson prologue: dx = omega*(invd*r) ; x += dx      (RichardsonSmoothers.jl:91-93)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) jacobi_step_kernel(int64_t n, const double *__restrict__ invd,
+                                                             const double *__restrict__ r, double omega,
+                                                             double *__restrict__ dx, double *__restrict__ x,
+                                                             int x_is_zero) {
+  for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * THREADS) {
+    const double d = __dmul_rn(omega, __dmul_rn(invd[i], r[i]));
+    dx[i] = d;
+    x[i] = x_is_zero ? __dadd_rn(0.0, d) : __dadd_rn(x[i], d);
+  }
+}
+
+// dot(a,b) over own values -> scal[slot]
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) dot_kernel(int64_t n, const double *__restrict__ a,
+                                                     const double *__restrict__ b, ReduceOut ro) {
+  __shared__ double red_smem[THREADS / 32];
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * THREADS)
+    acc = __dadd_rn(acc, __dmul_rn(a[i], b[i]));
+  double v[1] = {acc};
+  grid_reduce_finish<THREADS, 1>(v, ro, red_smem);
+}
+
+// z = invd .* r ; scal[slot] = dot(z, r)        (Jacobi Pl fused with CG's gamma, CGSolvers.jl:94-95)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) jacobi_dot_kernel(int64_t n, const double *__restrict__ invd,
+                                                            const double *__restrict__ r, double *__restrict__ z,
+                                                            ReduceOut ro) {
+  __shared__ double red_smem[THREADS / 32];
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * THREADS) {
+    const double ri = r[i];
+    const double zi = __dmul_rn(invd[i], ri);
+    z[i] = zi;
+    acc = __dadd_rn(acc, __dmul_rn(zi, ri));
+  }
+  double v[1] = {acc};
+  grid_reduce_finish<THREADS, 1>(v, ro, red_smem);
+}
+
+// CG tail: x += alpha p ; r -= alpha w ; scal[slot] = r.r      (CGSolvers.jl:105-111)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) cg_update_kernel(int64_t n, ScalarRef alpha, const double *__restrict__ p,
+                                                           const double *__restrict__ w, double *__restrict__ x,
+                                                           double *__restrict__ r, ReduceOut ro) {
+  __shared__ double red_smem[THREADS / 32];
+  const double al = load_scalar(alpha, ro.scal);
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * THREADS) {
+    x[i] = __dadd_rn(x[i], __dmul_rn(al, p[i]));
+    const double ri = __dsub_rn(r[i], __dmul_rn(al, w[i]));
+    r[i] = ri;
+    acc = __dadd_rn(acc, __dmul_rn(ri, ri));
+  }
+  double v[1] = {acc};
+  grid_reduce_finish<THREADS, 1>(v, ro, red_smem);
+}
+
+// gather / scatter for halo exchange
+__global__ void pack_kernel(int64_t n, const int *__restrict__ ids, const double *__restrict__ v, double *__restrict__ buf) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) buf[i] = v[ids[i]];
+}
+__global__ void unpack_kernel(int64_t n, const int *__restrict__ ids, const double *__restrict__ buf, double *__restrict__ v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[ids[i]] = buf[i];
+}
+
+// diag extraction: invd[i] = 1/A[i,i]  (JacobiLinearSolvers.jl:20-23,29-34; own-own block)
+__global__ void inv_diag_kernel(int64_t nrows, const int *__restrict__ rowptr, const int *__restrict__ col,
+                                const double *__restrict__ val, double *__restrict__ invd) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows) return;
+  double d = 0.0;  // diag() of a sparse matrix returns 0 for a missing entry
+  for (int e = rowptr[i]; e < rowptr[i + 1]; ++e)
+    if (col[e] == i) d = val[e];
+  invd[i] = __ddiv_rn(1.0, d);
+}
+
+// ------------------------------------------------------------------------------------------
+// dense coarse-level solver: Gauss-Jordan inverse with partial pivoting on the device (set-up),
+// applied as a GEMV (HBM-bound: n^2*8 bytes) -- the "small coarse-level solve kept on-device".
+__global__ void csr_to_dense_kernel(int64_t nrows, int64_t row_off, int64_t ld, const int *__restrict__ rowptr,
+                                    const int *__restrict__ col, const int64_t *__restrict__ col_gid,
+                                    const double *__restrict__ val, double *__restrict__ M) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows) return;
+  for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) {
+    const int64_t j = col_gid ? col_gid[col[e]] : col[e];
+    M[(row_off + i) * ld + j] = val[e];
+  }
+}
+__global__ void gj_set_identity_kernel(int64_t n, double *__restrict__ M) {  // right half of [A | I]
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) M[i * 2 * n + n + i] = 1.0;
+}
+// one block: pivot = argmax_{i>=k} |M[i][k]|
+__global__ void gj_pivot_kernel(int64_t n, int64_t k, const double *__restrict__ M, int *__restrict__ piv,
+                                double *__restrict__ pivval) {
+  __shared__ double sv[256];
+  __shared__ int si[256];
+  double best = -1.0;
+  int bi = (int)k;
+  for (int64_t i = k + threadIdx.x; i < n; i += blockDim.x) {
+    const double v = fabs(M[i * 2 * n + k]);
+    if (v > best) { best = v; bi = (int)i; }
+  }
+  sv[threadIdx.x] = best;
+  si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      if (sv[threadIdx.x + o] > sv[threadIdx.x] ||
+          (sv[threadIdx.x + o] == sv[threadIdx.x] && si[threadIdx.x + o] < si[threadIdx.x])) {
+        sv[threadIdx.x] = sv[threadIdx.x + o];
+        si[threadIdx.x] = si[threadIdx.x + o];
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    *piv = si[0];
+    *pivval = M[(int64_t)si[0] * 2 * n + k];
+  }
+}
+// factors of the elimination step, taken BEFORE the row swap: fcol[i] = M[i][k], and the row
+// that will hold old row k after the swap (row piv) gets old M[k][k]
+__global__ void gj_fcol_kernel(int64_t n, int64_t k, const double *__restrict__ M, const int *__restrict__ piv,
+                               double *__restrict__ fcol) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t p = *piv;
+  fcol[i] = (i == p) ? M[k * 2 * n + k] : M[i * 2 * n + k];
+}
+// prow = row piv / pivot ; row piv <- row k (row k itself is written by the eliminate kernel)
+__global__ void gj_swap_scale_kernel(int64_t n, int64_t k, double *__restrict__ M, const int *__restrict__ piv,
+                                     const double *__restrict__ pivval, double *__restrict__ prow) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= 2 * n) return;
+  const int64_t p = *piv;
+  const double a = M[p * 2 * n + j];
+  if (p != k) M[p * 2 * n + j] = M[k * 2 * n + j];
+  prow[j] = a / *pivval;
+}
+__global__ void gj_eliminate_kernel(int64_t n, int64_t k, double *__restrict__ M, const double *__restrict__ prow,
+                                    const double *__restrict__ fcol) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = blockIdx.y;
+  if (j >= 2 * n) return;
+  if (i == k) {
+    M[i * 2 * n + j] = prow[j];
+  } else {
+    const double f = fcol[i];
+    if (f != 0.0) M[i * 2 * n + j] -= f * prow[j];
+  }
+}
+__global__ void gj_extract_kernel(int64_t n, int64_t row0, int64_t nrows, const double *__restrict__ M,
+                                  double *__restrict__ inv) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = blockIdx.y;
+  if (j < n && i < nrows) inv[i * n + j] = M[(row0 + i) * 2 * n + n + j];
+}
+// y[i] = sum_j inv[i][j] * b[j]  : one warp per row, coalesced
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) dense_gemv_kernel(int64_t nrows, int64_t n, const double *__restrict__ inv,
+                                                            const double *__restrict__ b, double *__restrict__ y) {
+  const int64_t row = ((int64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= nrows) return;
+  const double *r = inv + row * n;
+  double s = 0.0;
+  for (int64_t j = lane; j < n; j += 32) s += r[j] * b[j];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) y[row] = s;
+}
+
+}  // namespace gsb

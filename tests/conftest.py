@@ -1,0 +1,25 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def gsb():
+    import gsb200
+
+    return gsb200
+
+
+@pytest.fixture(scope="session")
+def ctx(gsb):
+    """One device context for the whole GPU session (fails loudly without a GPU / the .so)."""
+    return gsb.Context.default()
