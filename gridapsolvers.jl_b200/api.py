@@ -87,6 +87,21 @@ class Context:
         check(_lib.lib().gsb_launch_count(self.h, ctypes.byref(n)))
         return int(n.value)
 
+    def profile_start(self):
+        check(_lib.lib().gsb_profile_start(self.h))
+
+    def profile_stop(self, cap: int = 256):
+        """-> list of dicts(mode, stream_kernel, nrows, nnz, count, total_ms) for the row kernels"""
+        n = ctypes.c_int()
+        mode, st, cnt = (np.zeros(cap, dtype=np.int32) for _ in range(3))
+        nrows, nnz = (np.zeros(cap, dtype=np.int64) for _ in range(2))
+        ms = np.zeros(cap)
+        check(_lib.lib().gsb_profile_stop(self.h, cap, ctypes.byref(n), _ptr(mode), _ptr(st), _ptr(nrows), _ptr(nnz),
+                                          _ptr(cnt), _ptr(ms)))
+        names = {0: "spmv", 1: "residual", 2: "sweep", 3: "spmv_dot", 4: "spmv_add"}
+        return [dict(mode=names[int(mode[i])], stream_kernel=bool(st[i]), nrows=int(nrows[i]), nnz=int(nnz[i]),
+                     count=int(cnt[i]), total_ms=float(ms[i])) for i in range(n.value)]
+
     def close(self):
         if self.h:
             _lib.lib().gsb_finalize(self.h)
@@ -141,10 +156,24 @@ class SparseMatrix:
         A = sp.csr_matrix(A)
         return cls(ctx, A.shape[0], A.shape[1] - n_ghost_cols, n_ghost_cols, A.indptr, A.indices, A.data, fmt="csr", plan=plan)
 
+    def bench_rows(self, mode: str, reps: int = 20) -> float:
+        """average ms of one row-kernel launch (diagnostics / roofline numbers)"""
+        ms = ctypes.c_float()
+        k = {"spmv": 0, "residual": 1, "sweep": 2, "spmv_dot": 3, "spmv_add": 4}[mode]
+        check(_lib.lib().gsb_bench_rows(self.h, k, reps, ctypes.byref(ms)))
+        return float(ms.value)
+
     def update_values(self, vals):
         vals = np.ascontiguousarray(vals, dtype=np.float64)
         assert vals.shape[0] == self.nnz
         check(_lib.lib().gsb_mat_update_values(self.h, _ptr(vals)))
+
+    def __del__(self):
+        try:
+            if self.h:
+                _lib.lib().gsb_mat_destroy(self.h)
+        except Exception:
+            pass
 
 
 class BlockSparseMatrix:

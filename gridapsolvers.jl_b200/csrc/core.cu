@@ -1,5 +1,6 @@
 // core.cu -- context, device mirrors (plan / matrix / vector) and launchers of the sm_100a kernels.
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <numeric>
 #include <stdexcept>
@@ -214,6 +215,36 @@ static void launch_stream(gsb_mat_t A, RowArgs &a) {
   launched(ctx);
 }
 
+// warp-specialised variant: NW consumer warps + 1 producer warp, U gathers in flight per lane
+constexpr int WS_NW = 8;
+constexpr int WS_U = 9;
+template <int G, int MODE>
+static void launch_stream_ws(gsb_mat_t A, RowArgs &a) {
+  gsb_ctx_t ctx = A->ctx;
+  auto kern = csr_stream_ws_kernel<G, MODE, WS_NW, ST_RING_LOG2, ST_CHUNK_LOG2, WS_U>;
+  constexpr size_t smem = (size_t)(1 << ST_RING_LOG2) * 12 + (size_t)((1 << ST_RING_LOG2) >> ST_CHUNK_LOG2) * 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  StreamArgs m{A->rowptr.p, A->col.p, A->val.p, A->cta_rows.p, A->nnz_padded};
+  kern<<<A->n_ctas, (WS_NW + 1) * 32, smem, ctx->stream>>>(m, a);
+  launched(ctx);
+}
+
+constexpr int SELL_THREADS = 256;
+constexpr int SELL_U = 9;
+template <int MODE>
+static void launch_sell(gsb_mat_t A, RowArgs &a) {
+  gsb_ctx_t ctx = A->ctx;
+  const int64_t grid = std::max<int64_t>(1, (A->n_rows + SELL_THREADS - 1) / SELL_THREADS);
+  if (MODE == ROW_SPMV_DOT) GSB_CHECK((size_t)grid <= PARTIALS_CAP, "matrix too large for the fused dot");
+  SellArgs m{A->rowptr.p, A->sell_off.p, A->sell_col.p, A->sell_val.p, A->n_rows};
+  csr_sell_kernel<MODE, SELL_THREADS, SELL_U><<<(unsigned)grid, SELL_THREADS, 0, ctx->stream>>>(m, a);
+  launched(ctx);
+}
+
 template <int G, int MODE>
 static void launch_vector(gsb_mat_t A, RowArgs &a) {
   gsb_ctx_t ctx = A->ctx;
@@ -235,7 +266,32 @@ static void launch_rows(gsb_mat_t A, RowArgs &a) {
   if (pref == "vector") stream = false;
   else if (pref == "auto") stream = stream && A->n_rows >= (int64_t)std::stoll(ctx->opt("stream_min_rows", "65536"));
   if (A->n_rows == 0) stream = false;
-  if (stream) {
+  gsb_ctx_s::ProfRec rec{};
+  if (ctx->profiling) {
+    rec.mode = MODE; rec.stream = stream ? 1 : 0; rec.nrows = A->n_rows; rec.nnz = A->nnz;
+    GSB_CUDA(cudaEventCreate(&rec.e0));
+    GSB_CUDA(cudaEventCreate(&rec.e1));
+    GSB_CUDA(cudaEventRecord(rec.e0, ctx->stream));
+  }
+  struct ProfEnd {
+    gsb_ctx_t c; gsb_ctx_s::ProfRec *r;
+    ~ProfEnd() { if (c->profiling) { cudaEventRecord(r->e1, c->stream); c->prof.push_back(*r); } }
+  } prof_end{ctx, &rec};
+  const bool sell = A->sell_ok && (pref == "sell" || (pref == "auto" && A->n_rows >= (int64_t)std::stoll(ctx->opt("sell_min_rows", "1"))));
+  rec.stream = sell ? 2 : rec.stream;
+  if (sell) {
+    launch_sell<MODE>(A, a);
+    return;
+  }
+  // the warp-specialised kernel needs a warp step (32/G rows) to fit half the ring
+  const bool ws_ok = (int64_t)A->max_row_nnz * (32 / A->G) <= ST_SPAN_MAX;
+  if (stream && ws_ok && ctx->opt("stream_kernel", "ws") == "ws") {
+    switch (A->G) {
+      case 1: launch_stream_ws<1, MODE>(A, a); break;
+      case 4: launch_stream_ws<4, MODE>(A, a); break;
+      default: launch_stream_ws<16, MODE>(A, a); break;
+    }
+  } else if (stream) {
     switch (A->G) {
       case 1: launch_stream<1, MODE>(A, a); break;
       case 4: launch_stream<4, MODE>(A, a); break;
@@ -555,6 +611,79 @@ int gsb_launch_count(gsb_ctx_t ctx, int64_t *out) {
   return GSB_OK;
 }
 
+int gsb_profile_start(gsb_ctx_t ctx) {
+  API_BEGIN
+  for (auto &r : ctx->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  ctx->prof.clear();
+  ctx->profiling = true;
+  API_END(ctx)
+}
+
+// aggregates the recorded row-kernel launches by (mode, kernel kind, rows, nnz)
+int gsb_profile_stop(gsb_ctx_t ctx, int cap, int *n_out, int *mode, int *stream, int64_t *nrows, int64_t *nnz,
+                     int *count, double *total_ms) {
+  API_BEGIN
+  ctx->profiling = false;
+  GSB_CUDA(cudaStreamSynchronize(ctx->stream));
+  int n = 0;
+  for (auto &r : ctx->prof) {
+    float ms = 0.f;
+    GSB_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    int k = 0;
+    for (; k < n; ++k)
+      if (mode[k] == r.mode && stream[k] == r.stream && nrows[k] == r.nrows && nnz[k] == r.nnz) break;
+    if (k == n) {
+      if (n == cap) continue;
+      mode[n] = r.mode; stream[n] = r.stream; nrows[n] = r.nrows; nnz[n] = r.nnz; count[n] = 0; total_ms[n] = 0.0;
+      ++n;
+    }
+    count[k] += 1;
+    total_ms[k] += ms;
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  ctx->prof.clear();
+  *n_out = n;
+  API_END(ctx)
+}
+
+// diagnostics: time `reps` back-to-back launches of one row-kernel mode on scratch vectors
+int gsb_bench_rows(gsb_mat_t A, int mode, int reps, float *avg_ms) {
+  API_BEGIN
+  gsb_ctx_t ctx = A->ctx;
+  GSB_CHECK(A->nb == 0 && reps >= 1, "bench_rows: bad arguments");
+  auto mk = [&](int64_t n_own, int64_t n_ghost, double v) {
+    std::unique_ptr<gsb_vec_s> p(new gsb_vec_s());
+    p->ctx = ctx; p->n_own = n_own; p->n_ghost = n_ghost;
+    GSB_CUDA(cudaMalloc(&p->d, sizeof(double) * std::max<int64_t>(1, n_own + n_ghost)));
+    std::vector<double> h((size_t)(n_own + n_ghost));
+    for (size_t i = 0; i < h.size(); ++i) h[i] = v * std::sin((double)i);
+    GSB_CUDA(cudaMemcpy(p->d, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice));
+    return p;
+  };
+  auto x = mk(A->n_own_cols, A->n_ghost_cols, 1.0), x2 = mk(A->n_own_cols, A->n_ghost_cols, 1.0);
+  auto y = mk(A->n_rows, 0, 1.0), r = mk(A->n_rows, 0, 1.0), xa = mk(A->n_rows, 0, 0.0), d = mk(A->n_rows, 0, 1e-3);
+  auto run = [&]() {
+    switch (mode) {
+      case ROW_SPMV: gsb::spmv(A, *x, *y, 1.0, 0.0); break;
+      case ROW_RESID: gsb::resid(A, *x, *r, *y); break;
+      case ROW_SWEEP: gsb::sweep(A, *x, *r, d->d, 2.0 / 3.0, *x2, *xa); break;
+      case ROW_SPMV_DOT: gsb::spmv_dot(A, *x, *y, *r, 1); break;
+      case ROW_SPMV_ADD: gsb::spmv_add(A, *x, *y, *xa); break;
+      default: fail(GSB_EINVAL, "bench_rows: unknown mode");
+    }
+  };
+  for (int i = 0; i < 3; ++i) run();
+  GSB_CUDA(cudaEventRecord(ctx->t0, ctx->stream));
+  for (int i = 0; i < reps; ++i) run();
+  GSB_CUDA(cudaEventRecord(ctx->t1, ctx->stream));
+  GSB_CUDA(cudaEventSynchronize(ctx->t1));
+  float ms = 0.f;
+  GSB_CUDA(cudaEventElapsedTime(&ms, ctx->t0, ctx->t1));
+  *avg_ms = ms / reps;
+  API_END(A->ctx)
+}
+
 int gsb_set_option(gsb_ctx_t ctx, const char *key, const char *value) {
   API_BEGIN
   ctx->opts[key] = value;
@@ -629,6 +758,43 @@ static void finish_matrix(gsb_mat_s *A, const std::vector<int> &rowptr, const st
   const double avg = A->n_rows ? (double)A->nnz / (double)A->n_rows : 0.0;
   A->G = avg <= 48.0 ? 1 : (avg <= 160.0 ? 4 : 16);
   A->stream_ok = mx <= ST_SPAN_MAX && A->n_rows > 0;
+  // SELL-32 mirror for one-lane-per-row matrices with little padding
+  A->sell_ok = false;
+  if (A->G == 1 && A->n_rows > 0 && ctx->opt("sell", "1") == "1") {
+    const int64_t nsl = (A->n_rows + 31) / 32;
+    std::vector<int> soff((size_t)nsl + 1, 0);
+    int64_t tot = 0;
+    for (int64_t sl = 0; sl < nsl; ++sl) {
+      int w = 0;
+      for (int64_t i = sl * 32; i < std::min<int64_t>(A->n_rows, sl * 32 + 32); ++i)
+        w = std::max(w, rowptr[(size_t)i + 1] - rowptr[(size_t)i]);
+      tot += w;
+      soff[(size_t)sl + 1] = (int)tot;
+    }
+    const int64_t entries = tot * 32;
+    if (tot < INT32_MAX && (double)entries <= 1.25 * (double)std::max<int64_t>(A->nnz, 1) + 4096) {
+      std::vector<int> sc((size_t)std::max<int64_t>(entries, 1), 0);
+      std::vector<double> sv((size_t)std::max<int64_t>(entries, 1), 0.0);
+#pragma omp parallel for schedule(static)
+      for (int64_t i = 0; i < A->n_rows; ++i) {
+        const size_t base = ((size_t)soff[(size_t)(i >> 5)] << 5) + (size_t)(i & 31);
+        const int e0 = rowptr[(size_t)i], n = rowptr[(size_t)i + 1] - e0;
+        for (int k = 0; k < n; ++k) {
+          sc[base + (size_t)k * 32] = col[(size_t)e0 + k];
+          sv[base + (size_t)k * 32] = val[(size_t)e0 + k];
+        }
+      }
+      A->sell_off.alloc(soff.size());
+      A->sell_col.alloc(sc.size());
+      A->sell_val.alloc(sv.size());
+      GSB_CUDA(cudaMemcpy(A->sell_off.p, soff.data(), sizeof(int) * soff.size(), cudaMemcpyHostToDevice));
+      GSB_CUDA(cudaMemcpy(A->sell_col.p, sc.data(), sizeof(int) * sc.size(), cudaMemcpyHostToDevice));
+      GSB_CUDA(cudaMemcpy(A->sell_val.p, sv.data(), sizeof(double) * sv.size(), cudaMemcpyHostToDevice));
+      A->sell_entries = entries;
+      A->sell_ok = true;
+      A->h_sell_off = soff;
+    }
+  }
   // persistent-CTA row partition balanced by nnz
   const int rows_per_step = ST_THREADS / A->G;
   int n_ctas = (int)std::min<int64_t>(ctx->num_sms, std::max<int64_t>(1, (A->n_rows + rows_per_step - 1) / rows_per_step));
@@ -714,12 +880,19 @@ int gsb_mat_create(gsb_ctx_t ctx, int64_t n_rows, int64_t n_own_cols, int64_t n_
 int gsb_mat_update_values(gsb_mat_t A, const double *vals) {
   API_BEGIN
   GSB_CHECK(A->nb == 0, "update_values: block matrix");
-  if (A->perm.empty()) {
-    GSB_CUDA(cudaMemcpy(A->val.p, vals, sizeof(double) * A->nnz, cudaMemcpyHostToDevice));
-  } else {
-    std::vector<double> v((size_t)A->nnz);
-    for (int64_t e = 0; e < A->nnz; ++e) v[(size_t)e] = vals[A->perm[(size_t)e]];
-    GSB_CUDA(cudaMemcpy(A->val.p, v.data(), sizeof(double) * A->nnz, cudaMemcpyHostToDevice));
+  std::vector<double> v((size_t)A->nnz);
+  for (int64_t e = 0; e < A->nnz; ++e) v[(size_t)e] = A->perm.empty() ? vals[e] : vals[A->perm[(size_t)e]];
+  if (A->nnz) GSB_CUDA(cudaMemcpy(A->val.p, v.data(), sizeof(double) * A->nnz, cudaMemcpyHostToDevice));
+  if (A->sell_ok) {
+    std::vector<int> rp((size_t)A->n_rows + 1);
+    GSB_CUDA(cudaMemcpy(rp.data(), A->rowptr.p, sizeof(int) * rp.size(), cudaMemcpyDeviceToHost));
+    std::vector<double> sv((size_t)std::max<int64_t>(A->sell_entries, 1), 0.0);
+    for (int64_t i = 0; i < A->n_rows; ++i) {
+      const size_t base = ((size_t)A->h_sell_off[(size_t)(i >> 5)] << 5) + (size_t)(i & 31);
+      const int e0 = rp[(size_t)i], n = rp[(size_t)i + 1] - e0;
+      for (int k = 0; k < n; ++k) sv[base + (size_t)k * 32] = v[(size_t)e0 + k];
+    }
+    GSB_CUDA(cudaMemcpy(A->sell_val.p, sv.data(), sizeof(double) * sv.size(), cudaMemcpyHostToDevice));
   }
   API_END(A->ctx)
 }

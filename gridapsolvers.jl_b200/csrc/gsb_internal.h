@@ -82,6 +82,10 @@ struct gsb_ctx_s {
   double *h_scal = nullptr;  // pinned host mirror for read-backs
   std::map<std::string, std::string> opts;
   std::string err;
+  // optional per-launch profiling of the row kernels (bench.py's roofline numbers)
+  struct ProfRec { int mode; int stream; int64_t nrows, nnz; cudaEvent_t e0, e1; };
+  bool profiling = false;
+  std::vector<ProfRec> prof;
   int alloc_slots(int n);
   double read_scalar(int slot);                 // blocking
   void read_scalars(int slot, int n, double *out);
@@ -128,6 +132,12 @@ struct gsb_mat_s {
   bool stream_ok = false;
   int n_ctas = 0;
   gsb::DevBuf<int> cta_rows;
+  // SELL-32 mirror (column-major slices of 32 rows), built when padding overhead is small
+  bool sell_ok = false;
+  int64_t sell_entries = 0;  // incl. padding
+  gsb::DevBuf<int> sell_off, sell_col;
+  std::vector<int> h_sell_off;
+  gsb::DevBuf<double> sell_val;
   // block matrix (acts on concatenated vectors)
   int nb = 0;
   std::vector<gsb_mat_t> blocks;  // row-major nb*nb, may contain nullptr

@@ -148,6 +148,126 @@ __global__ void __launch_bounds__(THREADS) csr_vector_kernel(int64_t nrows, cons
   }
 }
 
+template <int MODE>
+struct RowPre {  // epilogue operands, loaded before the gather loop so their latency is hidden
+  double b, invd, xacc, dotv;
+};
+template <int MODE>
+__device__ __forceinline__ void row_prefetch(const RowArgs &a, int64_t row, RowPre<MODE> &p) {
+  if (MODE == ROW_RESID) p.b = a.b[row];
+  if (MODE == ROW_SWEEP) { p.b = a.b[row]; p.invd = a.invd[row]; p.xacc = a.xacc[row]; }
+  if (MODE == ROW_SPMV_DOT) p.dotv = a.dotv[row];
+  if (MODE == ROW_SPMV_ADD) p.xacc = a.xacc[row];
+}
+template <int MODE>
+__device__ __forceinline__ void row_epilogue_pre(const RowArgs &a, int64_t row, double s, const RowPre<MODE> &p, double &acc) {
+  if (MODE == ROW_SPMV) {
+    a.y[row] = s;
+  } else if (MODE == ROW_RESID) {
+    a.out[row] = __dsub_rn(p.b, s);
+  } else if (MODE == ROW_SWEEP) {
+    const double r = __dsub_rn(p.b, s);
+    a.out[row] = r;
+    const double d = __dmul_rn(a.omega, __dmul_rn(p.invd, r));
+    a.dxout[row] = d;
+    a.xacc[row] = __dadd_rn(p.xacc, d);
+  } else if (MODE == ROW_SPMV_DOT) {
+    a.y[row] = s;
+    acc = __dadd_rn(acc, __dmul_rn(p.dotv, s));
+  } else if (MODE == ROW_SPMV_ADD) {
+    a.y[row] = s;
+    a.xacc[row] = __dadd_rn(p.xacc, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// SELL-32 kernel: the matrix is also kept in sliced-ELLPACK form with slice height 32 (one warp =
+// one slice, one lane = one row, entries of a slice stored column-major: entry k of the 32 rows
+// is contiguous).  Every matrix load of a warp is then one fully coalesced 256 B (values) /
+// 128 B (columns) transaction with addresses known in advance -- no row-pointer -> data
+// dependence, no shared-memory staging, no barriers -- and with one lane per row the gathers of x
+// are coalesced too and the row sum keeps the sequential ascending-column order (bit-exact with
+// the oracle).  Matrix data is streamed with L1::no_allocate so that L1 keeps x.
+__device__ __forceinline__ double ldg_stream_f64(const double *p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ldg_stream_s32(const int *p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+struct SellArgs {
+  const int *rowptr;      // CSR row pointers (row lengths)
+  const int *slice_off;   // per slice: offset of the slice in units of 32 entries; nslices+1 entries
+  const int *col;         // padded, column-major per slice
+  const double *val;
+  int64_t nrows;
+};
+
+template <int MODE, int THREADS, int U>
+__global__ void __launch_bounds__(THREADS) csr_sell_kernel(SellArgs m, RowArgs a) {
+  __shared__ double red_smem[THREADS / 32];
+  const int64_t row = (int64_t)blockIdx.x * THREADS + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t slice = row >> 5;
+  const int64_t nslices = (m.nrows + 31) >> 5;
+  double acc = 0.0;
+  if (slice < nslices) {  // warp-uniform
+    const bool valid = row < m.nrows;
+    const int so0 = m.slice_off[slice], so1 = m.slice_off[slice + 1];
+    const int width = so1 - so0;  // entries per row in this slice (warp-uniform)
+    int len = 0;
+    RowPre<MODE> pre{};
+    double s = 0.0;
+    if (valid) {
+      len = m.rowptr[row + 1] - m.rowptr[row];
+      row_prefetch<MODE>(a, row, pre);
+      s = row_init<MODE>(a, row);
+    }
+    const size_t base = ((size_t)so0 << 5) + lane;
+    const int *cp = m.col + base;
+    const double *vp = m.val + base;
+    const double al = a.alpha;
+    int k = 0;
+    for (; k + U <= width; k += U) {
+      int cc[U];
+      double vv[U], xv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        cc[u] = ldg_stream_s32(cp + (size_t)(k + u) * 32);
+        vv[u] = ldg_stream_f64(vp + (size_t)(k + u) * 32);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) xv[u] = __ldg(a.x + cc[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (k + u < len) {
+          double t = xv[u];
+          if (MODE == ROW_SPMV) t = __dmul_rn(t, al);
+          s = __dadd_rn(s, __dmul_rn(vv[u], t));
+        }
+      }
+    }
+    for (; k < width; ++k) {
+      const int c = ldg_stream_s32(cp + (size_t)k * 32);
+      const double v = ldg_stream_f64(vp + (size_t)k * 32);
+      double t = __ldg(a.x + c);
+      if (k < len) {
+        if (MODE == ROW_SPMV) t = __dmul_rn(t, al);
+        s = __dadd_rn(s, __dmul_rn(v, t));
+      }
+    }
+    if (valid) row_epilogue_pre<MODE>(a, row, s, pre, acc);
+  }
+  if (MODE == ROW_SPMV_DOT) {
+    double v[1] = {acc};
+    grid_reduce_finish<THREADS, 1>(v, a.red, red_smem);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + TMA 1-D bulk copy (cp.async.bulk, SASS: UBLKCP)
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -272,6 +392,140 @@ __global__ void __launch_bounds__(THREADS) csr_stream_kernel(StreamArgs m, RowAr
       }
       if (active && lane == 0) row_epilogue<MODE>(a, row, s, acc);
       g0 += n;
+    }
+  }
+  if (MODE == ROW_SPMV_DOT) {
+    double v[1] = {acc};
+    grid_reduce_finish<THREADS, 1>(v, a.red, red_smem);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// warp-specialised streaming CSR kernel (the production hot kernel).
+//   warp NW          : producer -- one lane streams the CTA's val[]/col[] slice through the ring
+//                      with TMA bulk copies, re-filling a slot as soon as every consumer warp has
+//                      released it (empty[] mbarriers, count NW)
+//   warps 0 .. NW-1  : consumers -- each owns every NW-th step of 32/G consecutive rows, waits on the
+//                      full[] mbarriers of the chunks its row touches, walks the row in batches of U
+//                      entries (U independent x-gathers in flight per lane), applies the fused
+//                      epilogue, then releases the chunks it has moved past.
+// There is no block-wide barrier in the main loop: warps drift apart by up to the ring capacity,
+// so DRAM streaming, shared-memory reads and L1/L2 gathers of different warps overlap.
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int G, int MODE, int NW, int RING_LOG2, int CHUNK_LOG2, int U>
+__global__ void __launch_bounds__((NW + 1) * 32, 1) csr_stream_ws_kernel(StreamArgs m, RowArgs a) {
+  constexpr int THREADS = (NW + 1) * 32;
+  constexpr int RING = 1 << RING_LOG2;
+  constexpr int CHUNK = 1 << CHUNK_LOG2;
+  constexpr int NSLOT = RING / CHUNK;
+  constexpr int RW = 32 / G;  // rows per warp step
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *sval = reinterpret_cast<double *>(smem_raw);
+  int *scol = reinterpret_cast<int *>(smem_raw + (size_t)RING * 8);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)RING * 12);
+  uint64_t *empty = full + NSLOT;
+  __shared__ double red_smem[(THREADS + 31) / 32];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int R0 = m.cta_rows[blockIdx.x], R1 = m.cta_rows[blockIdx.x + 1];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSLOT; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  double acc = 0.0;
+  if (R0 < R1) {
+    const int E0 = m.rowptr[R0], E1 = m.rowptr[R1];
+    const int S0 = E0 & ~3;  // 16-byte aligned start of this CTA's stream
+    const int nchunks = (E1 - S0 + CHUNK - 1) >> CHUNK_LOG2;
+    if (warp == NW) {
+      // ------------------------------------------------ producer
+      if (lane == 0) {
+        for (int c = 0; c < nchunks; ++c) {
+          const int slot = c & (NSLOT - 1);
+          if (c >= NSLOT) mbar_wait(&empty[slot], (uint32_t)(((c / NSLOT) - 1) & 1));
+          const int64_t start = (int64_t)S0 + ((int64_t)c << CHUNK_LOG2);
+          int64_t cnt = m.nnz_padded - start;
+          if (cnt > CHUNK) cnt = CHUNK;
+          mbar_expect_tx(&full[slot], (uint32_t)cnt * 12u);
+          tma_bulk_g2s(sval + (size_t)slot * CHUNK, m.val + start, (uint32_t)cnt * 8u, &full[slot]);
+          tma_bulk_g2s(scol + (size_t)slot * CHUNK, m.col + start, (uint32_t)cnt * 4u, &full[slot]);
+        }
+      }
+    } else {
+      // ------------------------------------------------ consumers
+      const int sub = lane / G, gl = lane % G;
+      int released = 0;  // meaningful in lane 0
+      int first = R0 + warp * RW;  // first row of this warp's current step
+      int row = first + sub;
+      int rp0 = 0, rp1 = 0;
+      if (row < R1) { rp0 = m.rowptr[row]; rp1 = m.rowptr[row + 1]; }
+      while (first < R1) {
+        const bool valid = row < R1;
+        RowPre<MODE> pre{};
+        if (valid && gl == 0) row_prefetch<MODE>(a, row, pre);
+        // row pointers of this warp's next step
+        const int nfirst = first + NW * RW, nrow = nfirst + sub;
+        int nrp0 = 0, nrp1 = 0;
+        if (nrow < R1) { nrp0 = m.rowptr[nrow]; nrp1 = m.rowptr[nrow + 1]; }
+        double s = 0.0;
+        if (valid) {
+          const int e0 = rp0, e1 = rp1;
+          if (e1 > e0) {
+            const int c0 = (e0 - S0) >> CHUNK_LOG2, c1 = (e1 - 1 - S0) >> CHUNK_LOG2;
+            for (int c = c0; c <= c1; ++c) mbar_wait(&full[c & (NSLOT - 1)], (uint32_t)((c / NSLOT) & 1));
+          }
+          if (gl == 0) s = row_init<MODE>(a, row);
+          const double al = a.alpha;
+          for (int k = e0 + gl; k < e1; k += U * G) {
+            int cc[U];
+            double vv[U], xv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const int e = k + u * G;
+              const int p = (e - S0) & (RING - 1);
+              cc[u] = (e < e1) ? scol[p] : 0;
+              vv[u] = (e < e1) ? sval[p] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) xv[u] = (k + u * G < e1) ? __ldg(a.x + cc[u]) : 0.0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              if (k + u * G < e1) {
+                double t = xv[u];
+                if (MODE == ROW_SPMV) t = __dmul_rn(t, al);
+                s = __dadd_rn(s, __dmul_rn(vv[u], t));
+              }
+            }
+          }
+        }
+        if (G > 1) {
+#pragma unroll
+          for (int o = G / 2; o > 0; o >>= 1) s = __dadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
+        }
+        if (valid && gl == 0) row_epilogue_pre<MODE>(a, row, s, pre, acc);
+        // release the chunks this warp has moved past
+        const int e_next = __shfl_sync(0xffffffffu, (nfirst < R1) ? nrp0 : E1, 0);
+        const int pass = (nfirst < R1) ? ((e_next - S0) >> CHUNK_LOG2) : nchunks;
+        __syncwarp();
+        // (a chunk is released only once it has landed: a warp that skips a chunk must not arrive
+        //  on empty[] before the slot's previous use has been released by every warp, or its
+        //  arrival would be counted in the wrong phase)
+        if (lane == 0)
+          for (; released < pass; ++released) {
+            mbar_wait(&full[released & (NSLOT - 1)], (uint32_t)((released / NSLOT) & 1));
+            mbar_arrive(&empty[released & (NSLOT - 1)]);
+          }
+        first = nfirst; row = nrow; rp0 = nrp0; rp1 = nrp1;
+      }
+      if (lane == 0)
+        for (; released < nchunks; ++released) {
+          mbar_wait(&full[released & (NSLOT - 1)], (uint32_t)((released / NSLOT) & 1));
+          mbar_arrive(&empty[released & (NSLOT - 1)]);
+        }
     }
   }
   if (MODE == ROW_SPMV_DOT) {

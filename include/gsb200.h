@@ -62,6 +62,13 @@ int gsb_timer_start(gsb_ctx_t ctx);
 int gsb_timer_stop(gsb_ctx_t ctx, float *ms);
 /* number of kernels this library has launched on this context so far */
 int gsb_launch_count(gsb_ctx_t ctx, int64_t *out);
+/* per-launch CUDA-event timing of the row kernels (SpMV / residual / sweep / transfer), aggregated
+ * by (mode, kernel kind, rows, nnz); mode = 0 spmv, 1 residual, 2 fused sweep, 3 spmv+dot, 4 spmv+add */
+int gsb_profile_start(gsb_ctx_t ctx);
+int gsb_profile_stop(gsb_ctx_t ctx, int cap, int *n_out, int *mode, int *stream_kernel, int64_t *nrows, int64_t *nnz,
+                     int *count, double *total_ms);
+/* diagnostics: average duration of `reps` back-to-back launches of one row-kernel mode on scratch vectors */
+int gsb_bench_rows(gsb_mat_t A, int mode, int reps, float *avg_ms);
 /* runtime knobs, "key=value" (e.g. "spmv=stream", "spmv=vector", "graph=0"); for tests/tuning */
 int gsb_set_option(gsb_ctx_t ctx, const char *key, const char *value);
 

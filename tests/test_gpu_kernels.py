@@ -22,7 +22,7 @@ def _rand(n, seed):
 
 
 @pytest.mark.parametrize("nc", [(8, 8), (33, 17), (8, 8, 8), (20, 24, 16)])
-@pytest.mark.parametrize("kernel", ["vector", "stream"])
+@pytest.mark.parametrize("kernel", ["vector", "stream", "sell"])
 def test_spmv_bit_exact(gsb, ctx, nc, kernel):
     ctx.set_option("spmv", kernel)
     try:
@@ -44,6 +44,42 @@ def test_spmv_bit_exact(gsb, ctx, nc, kernel):
             assert np.array_equal(yd.get(), yo), (alpha, beta)
     finally:
         ctx.set_option("spmv", "auto")
+
+
+@pytest.mark.parametrize("stream_kernel", ["ws", "v1"])
+@pytest.mark.parametrize("nc", [(64, 64, 64), (96, 80, 72), (700, 600)])
+def test_stream_ring_wraparound_bit_exact(gsb, ctx, nc, stream_kernel):
+    """sizes at which every persistent CTA wraps its shared-memory ring several times and the
+    consumer warps drift apart: SpMV, residual and fused sweeps stay bit-identical to the oracle"""
+    from gsb200 import synth
+    from util import host_to_scipy
+
+    ctx.set_option("spmv", "stream")
+    ctx.set_option("stream_kernel", stream_kernel)
+    try:
+        hh = synth.poisson_hierarchy_host(nc, 1)
+        n = hh.levels[0].n_own
+        As = host_to_scipy(hh.A[0], n)
+        A, Ao = dev_matrix(gsb, ctx, As), ola.CSR(As)
+        x = _rand(n, 21)
+        xd, yd = dev_vec(gsb, A, x), dev_vec(gsb, A, domain=False)
+        yo = np.zeros(n)
+        ola.mul(yo, Ao, x)
+        for _ in range(3):
+            gsb.mul_(yd, A, xd)
+            assert np.array_equal(yd.get(), yo)
+        s = gsb.RichardsonSmoother(gsb.JacobiLinearSolver(), 4, 2.0 / 3.0)
+        ns = gsb.numerical_setup(gsb.symbolic_setup(s, A), A)
+        x0, r0 = _rand(n, 22), _rand(n, 23)
+        xd, rd = dev_vec(gsb, A, x0), dev_vec(gsb, A, r0)
+        gsb.solve_(xd, ns, rd)
+        so = OS.RichardsonSmoother(OS.JacobiLinearSolver(), 4, 2.0 / 3.0)
+        xo, ro = x0.copy(), r0.copy()
+        OS.solve_(xo, OS.numerical_setup(OS.symbolic_setup(so, Ao), Ao), ro)
+        assert np.array_equal(xd.get(), xo) and np.array_equal(rd.get(), ro)
+    finally:
+        ctx.set_option("spmv", "auto")
+        ctx.set_option("stream_kernel", "ws")
 
 
 def test_spmv_csc_int64_one_based_upload(gsb, ctx):
@@ -90,7 +126,7 @@ def test_spmv_unsorted_rows_and_empty_rows(gsb, ctx):
 
 
 @pytest.mark.parametrize("G_rows", [60, 200])  # average row length selects 4 / 16 lanes per row
-@pytest.mark.parametrize("kernel", ["vector", "stream"])
+@pytest.mark.parametrize("kernel", ["vector", "stream", "sell"])
 def test_spmv_long_rows(gsb, ctx, G_rows, kernel):
     ctx.set_option("spmv", kernel)
     try:
@@ -125,7 +161,7 @@ def test_blas1(gsb, ctx):
 
 
 @pytest.mark.parametrize("nc", [(16, 16), (12, 12, 12)])
-@pytest.mark.parametrize("kernel", ["vector", "stream"])
+@pytest.mark.parametrize("kernel", ["vector", "stream", "sell"])
 def test_richardson_jacobi_bit_exact(gsb, ctx, nc, kernel):
     """fused Jacobi-Richardson sweeps == reference statement sequence (RichardsonSmoothers.jl:84-98)"""
     ctx.set_option("spmv", kernel)
