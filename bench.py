@@ -292,7 +292,7 @@ def main():
     kernels = []
     for p in res.get("prof", []):
         t = p["total_ms"] / p["count"] * 1e-3
-        kernels.append({"kernel": p["mode"], "tma_stream": p["stream_kernel"], "rows": p["nrows"], "nnz": p["nnz"],
+        kernels.append({"kernel": p["mode"], "impl": p["impl"], "rows": p["nrows"], "nnz": p["nnz"],
                         "launches": p["count"], "avg_us": round(t * 1e6, 2),
                         "GBps": round(algo_bytes(p["mode"], p["nrows"], p["nnz"]) / t / 1e9, 1),
                         "share_of_solve": round(p["total_ms"] / res["ms"], 4)})
@@ -300,7 +300,7 @@ def main():
     top = next((k for k in kernels if k["kernel"] == "sweep" and k["rows"] == res["rows"][0]), kernels[0] if kernels else None)
     roofline = None
     if top:
-        roofline = {"bound": "hbm", "kernel": "csr_stream_kernel<sweep> level 1 (fused Jacobi-Richardson sweep)",
+        roofline = {"bound": "hbm", "kernel": "csr_sell_kernel<sweep> level 1 (fused Jacobi-Richardson sweep, SELL-32)",
                     "achieved": top["GBps"], "peak": peak, "unit": "GB/s", "frac": round(top["GBps"] / peak, 4),
                     "frac_of_nominal_8TBs": round(top["GBps"] / 8000.0, 4), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": algo_bytes("sweep", top["rows"], top["nnz"]),

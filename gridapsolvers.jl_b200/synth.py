@@ -220,6 +220,17 @@ def exact_solution(lp: LevelPart):
     return X[:, 0] * h[0] + (X[:, 1] * h[1] if lp.d > 1 else 0.0)
 
 
+def lexicographic_ids(lp: LevelPart):
+    """global lexicographic free-dof id (the serial numbering) of every local dof (own, then ghost)."""
+    X = _box_coords(lp.elo, lp.ehi)
+    keep = lp.ext_lid >= 0
+    ninner = np.array(lp.ncell, dtype=np.int64) - 1
+    gid = _box_lids(np.ones(lp.d, dtype=np.int64), ninner + 1, X[keep])
+    out = np.empty(lp.n_own + lp.n_ghost, dtype=np.int64)
+    out[lp.ext_lid[keep]] = gid
+    return out
+
+
 def to_scipy(rowptr, col, val, ncols):
     import scipy.sparse as sp
 

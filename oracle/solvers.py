@@ -48,11 +48,11 @@ class SolverTolerances:
 
 
 def converged(tols, niter, e_a, e_r):  # SolverTolerances.jl:126-128
-    return (e_r < tols.rtol) or (e_a < tols.atol)
+    return bool((e_r < tols.rtol) or (e_a < tols.atol))
 
 
 def finished(tols, niter, e_a, e_r):  # SolverTolerances.jl:117-119
-    return (niter >= tols.maxiter) or converged(tols, niter, e_a, e_r)
+    return bool((niter >= tols.maxiter) or converged(tols, niter, e_a, e_r))
 
 
 def finished_flag(tols, niter, e_a, e_r):  # SolverTolerances.jl:97-110
