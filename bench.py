@@ -28,6 +28,10 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: keep NCCL's banner / debug output on stderr
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 PARTS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
 RTOL, ATOL, MAXITER = 1e-8, 1e-14, 100
@@ -218,7 +222,7 @@ def main():
         nlev = n_levels(cells, world)
         ncell = tuple(cells * p for p in parts)
         t0 = time.perf_counter()
-        hh = synth.poisson_hierarchy_host(ncell, nlev, parts=parts, rank=rank)
+        hh = synth.poisson_hierarchy_host(ncell, nlev, parts=parts, rank=rank, lengths=tuple(float(p) for p in parts))
         t_gen = time.perf_counter() - t0
         t0 = time.perf_counter()
         dh = synth.upload_hierarchy(ctx, hh)
@@ -329,7 +333,8 @@ def main():
         "config": {
             "workload": (f"{'C2' if (world == 1 and cells == 128) else 'C3-style weak scaling'}: CGSolver(GMGLinearSolver V-cycle, "
                          f"{res['nlev']} levels, RichardsonSmoother(Jacobi,10,2/3) pre+post, LU coarse, maxiter=1) on 3D Poisson Q1, "
-                         f"{'x'.join(str(c) for c in res['ncell'])} cells = {n_glob} DOFs, {cells}^3 cells per GPU, rtol 1e-8, x0=0"),
+                         f"{'x'.join(str(c) for c in res['ncell'])} cells on [0,{PARTS[world][0]}]x[0,{PARTS[world][1]}]x[0,{PARTS[world][2]}] (cubic cells) = {n_glob} DOFs, "
+                         f"{cells}^3 cells per GPU, rtol 1e-8, x0=0"),
             "partition": "x".join(str(p) for p in PARTS[world]), "levels_rows_rank0": res["rows"], "levels_nnz_rank0": res["nnz"],
             "l2_policy": "inputs larger than L2 (fine-level CSR matrix %.0f MB >> 126 MB L2); coarse levels are L2-resident by construction" % (12 * res["nnz"][0] / 1e6),
             "setup_s": round(res["t_setup"], 3), "host_generation_s": round(res["t_gen"], 3),

@@ -147,7 +147,7 @@ def synth():
         if not os.path.exists(SYNTH_PATH):
             raise RuntimeError(f"{SYNTH_PATH} is missing: run build()")
         S = ctypes.CDLL(SYNTH_PATH)
-        rows = [c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p]
+        rows = [c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p]
         S.synth_poisson_rows.argtypes = rows + [c_p]
         S.synth_mass_rows.argtypes = rows
         tr = [c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p]

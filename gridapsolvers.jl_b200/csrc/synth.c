@@ -3,7 +3,7 @@
  *
  * NOT part of the solve path: it plays the role of the Gridap/GridapDistributed assembly the
  * Julia host performs before calling the solvers (SURVEY.md 8d "Concrete synthetic inputs"):
- * Q1 Poisson on a uniform Cartesian mesh of [0,1]^d, Dirichlet on the whole boundary,
+ * Q1 Poisson on a uniform Cartesian mesh of [0,L1]x..x[0,Ld] (L = 1 by default), Dirichlet on the whole boundary,
  * manufactured u = x + y (test/LinearSolvers/KrylovTests.jl:11-12,46-61, GMGTests.jl:204-215),
  * and the factor-2 nodal prolongation / its transpose between nested levels
  * (src/MultilevelTools/GridTransferOperators.jl:391-401,536-561).  Each rank generates only its
@@ -45,12 +45,12 @@ static void sort_row(int n, int32_t *c, double *v) {
 /* rows of the Q1 Laplacian for the own box [olo,ohi) (global node coords), and the Dirichlet
  * lift b_i = -sum_{j Dirichlet} A_ij (x_j + y_j).  rowptr has n_own+1 entries.
  * pass 0: fill rowptr counts (rowptr[i+1] = nnz of row i, caller prefix-sums); pass 1: fill. */
-void synth_poisson_rows(int d, const int64_t *ncell, const int64_t *elo, const int64_t *ehi, const int32_t *ext_lid,
+void synth_poisson_rows(int d, const int64_t *ncell, const double *lengths, const int64_t *elo, const int64_t *ehi, const int32_t *ext_lid,
                         const int64_t *olo, const int64_t *ohi, int pass, int64_t *rowptr, int32_t *col, double *val,
                         double *b) {
   double h[MAXD], kd[MAXD][3], md[MAXD][3];
   for (int k = 0; k < d; ++k) {
-    h[k] = 1.0 / (double)ncell[k];
+    h[k] = lengths[k] / (double)ncell[k];
     kd[k][0] = kd[k][2] = -1.0 / h[k];
     kd[k][1] = 2.0 / h[k];
     md[k][0] = md[k][2] = h[k] / 6.0;
@@ -108,11 +108,11 @@ void synth_poisson_rows(int d, const int64_t *ncell, const int64_t *elo, const i
 }
 
 /* mass-matrix rows (for L2 errors in the known-answer tests); same calling convention */
-void synth_mass_rows(int d, const int64_t *ncell, const int64_t *elo, const int64_t *ehi, const int32_t *ext_lid,
+void synth_mass_rows(int d, const int64_t *ncell, const double *lengths, const int64_t *elo, const int64_t *ehi, const int32_t *ext_lid,
                      const int64_t *olo, const int64_t *ohi, int pass, int64_t *rowptr, int32_t *col, double *val) {
   double h[MAXD], md[MAXD][3];
   for (int k = 0; k < d; ++k) {
-    h[k] = 1.0 / (double)ncell[k];
+    h[k] = lengths[k] / (double)ncell[k];
     md[k][0] = md[k][2] = h[k] / 6.0;
     md[k][1] = 2.0 * h[k] / 3.0;
   }

@@ -65,6 +65,7 @@ class LevelPart:
     n_ghost: int
     ghost_owner: np.ndarray
     ghost_owner_lid: np.ndarray
+    lengths: tuple = None  # domain edge lengths (default 1.0 each)
     nbr_snd: np.ndarray = field(default=None)
     snd_ptrs: np.ndarray = field(default=None)
     snd_ids: np.ndarray = field(default=None)
@@ -105,7 +106,7 @@ def _box_coords(lo, hi):
     return np.stack([g.ravel(order="F") for g in grids], axis=1)
 
 
-def make_level_part(ncell, parts, rank) -> LevelPart:
+def make_level_part(ncell, parts, rank, lengths=None) -> LevelPart:
     ncell, parts = tuple(int(n) for n in ncell), tuple(int(p) for p in parts)
     d = len(ncell)
     pc = part_coords(rank, parts)
@@ -142,7 +143,8 @@ def make_level_part(ncell, parts, rank) -> LevelPart:
     gl[order] = n_own + np.arange(G.shape[0])
     ext_lid[ghost] = gl
     lp = LevelPart(ncell, parts, rank, olo, ohi, elo, ehi, ext_lid.astype(np.int32), n_own, int(G.shape[0]),
-                   owner[order].astype(np.int32), owner_lid[order])
+                   owner[order].astype(np.int32), owner_lid[order],
+                   tuple(float(v) for v in (lengths if lengths is not None else (1.0,) * d)))
     # receive lists: ghosts grouped by owner (already sorted)
     nbr_rcv, counts = np.unique(lp.ghost_owner, return_counts=True)
     lp.nbr_rcv = nbr_rcv.astype(np.int32)
@@ -190,14 +192,16 @@ def poisson_rows(lp: LevelPart):
     """(rowptr, col, val, b) of this part's rows of the Q1 Laplacian + Dirichlet lift of u=x+y."""
     S = _lib.synth()
     nc = np.array(lp.ncell, dtype=np.int64)
-    return _two_pass(S.synth_poisson_rows, lp.n_own, lp.d, _p(nc), _p(lp.elo), _p(lp.ehi), _p(lp.ext_lid), _p(lp.olo),
+    L = np.array(lp.lengths, dtype=np.float64)
+    return _two_pass(S.synth_poisson_rows, lp.n_own, lp.d, _p(nc), _p(L), _p(lp.elo), _p(lp.ehi), _p(lp.ext_lid), _p(lp.olo),
                      _p(lp.ohi), with_b=True)
 
 
 def mass_rows(lp: LevelPart):
     S = _lib.synth()
     nc = np.array(lp.ncell, dtype=np.int64)
-    return _two_pass(S.synth_mass_rows, lp.n_own, lp.d, _p(nc), _p(lp.elo), _p(lp.ehi), _p(lp.ext_lid), _p(lp.olo),
+    L = np.array(lp.lengths, dtype=np.float64)
+    return _two_pass(S.synth_mass_rows, lp.n_own, lp.d, _p(nc), _p(L), _p(lp.elo), _p(lp.ehi), _p(lp.ext_lid), _p(lp.olo),
                      _p(lp.ohi))[:3]
 
 
@@ -216,7 +220,7 @@ def restrict_rows(fine: LevelPart, coarse: LevelPart):
 def exact_solution(lp: LevelPart):
     """nodal values of u = x + y at the own dofs."""
     X = _box_coords(lp.olo, lp.ohi).astype(np.float64)
-    h = 1.0 / np.array(lp.ncell, dtype=np.float64)
+    h = np.array(lp.lengths, dtype=np.float64) / np.array(lp.ncell, dtype=np.float64)
     return X[:, 0] * h[0] + (X[:, 1] * h[1] if lp.d > 1 else 0.0)
 
 
@@ -248,14 +252,14 @@ class HostHierarchy:
     b: np.ndarray
 
 
-def poisson_hierarchy_host(ncell_fine, nlevels, parts=None, rank=0) -> HostHierarchy:
+def poisson_hierarchy_host(ncell_fine, nlevels, parts=None, rank=0, lengths=None) -> HostHierarchy:
     d = len(ncell_fine)
     parts = tuple(parts) if parts is not None else (1,) * d
     levels, As = [], []
     nc = tuple(int(n) for n in ncell_fine)
     b0 = None
     for l in range(nlevels):
-        lp = make_level_part(nc, parts, rank)
+        lp = make_level_part(nc, parts, rank, lengths)
         rowptr, col, val, b = poisson_rows(lp)
         if l == 0:
             b0 = b
