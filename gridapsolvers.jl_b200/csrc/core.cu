@@ -1,6 +1,7 @@
 // core.cu -- context, device mirrors (plan / matrix / vector) and launchers of the sm_100a kernels.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <stdexcept>
@@ -172,32 +173,58 @@ void inv_diag(gsb_mat_t A, double *invd) {
 }
 
 // ---------------------------------------------------------------- halo exchange (consistent!)
-void consistent(gsb_vec_s &v, gsb_plan_t plan) {
+static bool plan_active(gsb_vec_s &v, gsb_plan_t plan) {
   gsb_ctx_t ctx = v.ctx;
-  if (!plan || ctx->nranks == 1) return;
-  if (plan->nbr_snd.empty() && plan->nbr_rcv.empty()) return;
+  if (!plan || ctx->nranks == 1) return false;
+  if (plan->nbr_snd.empty() && plan->nbr_rcv.empty()) return false;
   GSB_CHECK(v.n_own == plan->n_own && v.n_ghost == plan->n_ghost, "consistent!: vector does not match the plan");
+  return true;
+}
+
+static void exchange_on(gsb_vec_s &v, gsb_plan_t plan, cudaStream_t st) {
+  gsb_ctx_t ctx = v.ctx;
   const int64_t nsnd = plan->snd_ptrs.back(), nrcv = plan->rcv_ptrs.back();
   if (nsnd) {
     int grid = (int)std::min<int64_t>((nsnd + 255) / 256, 1024);
-    pack_kernel<<<grid, 256, 0, ctx->stream>>>(nsnd, plan->snd_ids.p, v.d, plan->snd_buf.p);
+    pack_kernel<<<grid, 256, 0, st>>>(nsnd, plan->snd_ids.p, v.d, plan->snd_buf.p);
     launched(ctx);
   }
   GSB_NCCL(ncclGroupStart());
   for (size_t k = 0; k < plan->nbr_rcv.size(); ++k) {
     const int64_t off = plan->rcv_ptrs[k], cnt = plan->rcv_ptrs[k + 1] - off;
-    if (cnt) GSB_NCCL(ncclRecv(plan->rcv_buf.p + off, cnt, ncclDouble, plan->nbr_rcv[k], ctx->comm, ctx->stream));
+    if (cnt) GSB_NCCL(ncclRecv(plan->rcv_buf.p + off, cnt, ncclDouble, plan->nbr_rcv[k], ctx->comm, st));
   }
   for (size_t k = 0; k < plan->nbr_snd.size(); ++k) {
     const int64_t off = plan->snd_ptrs[k], cnt = plan->snd_ptrs[k + 1] - off;
-    if (cnt) GSB_NCCL(ncclSend(plan->snd_buf.p + off, cnt, ncclDouble, plan->nbr_snd[k], ctx->comm, ctx->stream));
+    if (cnt) GSB_NCCL(ncclSend(plan->snd_buf.p + off, cnt, ncclDouble, plan->nbr_snd[k], ctx->comm, st));
   }
   GSB_NCCL(ncclGroupEnd());
   if (nrcv) {
     int grid = (int)std::min<int64_t>((nrcv + 255) / 256, 1024);
-    unpack_kernel<<<grid, 256, 0, ctx->stream>>>(nrcv, plan->rcv_ids.p, plan->rcv_buf.p, v.d);
+    unpack_kernel<<<grid, 256, 0, st>>>(nrcv, plan->rcv_ids.p, plan->rcv_buf.p, v.d);
     launched(ctx);
   }
+}
+
+void consistent(gsb_vec_s &v, gsb_plan_t plan) {
+  if (!plan_active(v, plan)) return;
+  exchange_on(v, plan, v.ctx->stream);
+}
+
+// overlap: the exchange runs on the communication stream, ordered after everything already queued
+// on the compute stream (which produced v) ...
+void consistent_begin(gsb_vec_s &v, gsb_plan_t plan) {
+  if (!plan_active(v, plan)) return;
+  gsb_ctx_t ctx = v.ctx;
+  GSB_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
+  GSB_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_a, 0));
+  exchange_on(v, plan, ctx->comm_stream);
+  GSB_CUDA(cudaEventRecord(ctx->ev_b, ctx->comm_stream));
+}
+// ... and the compute stream waits for the ghosts only before the ghost-column pass
+void consistent_end(gsb_vec_s &v, gsb_plan_t plan) {
+  if (!plan_active(v, plan)) return;
+  GSB_CUDA(cudaStreamWaitEvent(v.ctx->stream, v.ctx->ev_b, 0));
 }
 
 // ---------------------------------------------------------------- row kernels
@@ -236,13 +263,60 @@ static void launch_stream_ws(gsb_mat_t A, RowArgs &a) {
 constexpr int SELL_THREADS = 256;
 constexpr int SELL_U = 9;
 template <int MODE>
-static void launch_sell(gsb_mat_t A, RowArgs &a) {
+static void launch_sell_list(gsb_mat_t A, RowArgs &a, const int *list, int64_t n_list) {
   gsb_ctx_t ctx = A->ctx;
-  const int64_t grid = std::max<int64_t>(1, (A->n_rows + SELL_THREADS - 1) / SELL_THREADS);
+  if (n_list == 0 && MODE != ROW_SPMV_DOT) return;
+  const int64_t grid = std::max<int64_t>(1, (n_list * 32 + SELL_THREADS - 1) / SELL_THREADS);
   if (MODE == ROW_SPMV_DOT) GSB_CHECK((size_t)grid <= PARTIALS_CAP, "matrix too large for the fused dot");
-  SellArgs m{A->rowptr.p, A->sell_off.p, A->sell_col.p, A->sell_val.p, A->n_rows};
-  csr_sell_kernel<MODE, SELL_THREADS, SELL_U><<<(unsigned)grid, SELL_THREADS, 0, ctx->stream>>>(m, a);
+  SellArgs m{list, n_list, A->rowptr.p, A->sell_off.p, A->sell_col.p, A->sell_val.p, A->n_rows};
+  const int variant = std::stoi(ctx->opt("sell_variant", "0"));
+#define GSB_SELL(U_, MINB_, STYLE_) \
+  csr_sell_kernel<MODE, SELL_THREADS, U_, MINB_, STYLE_><<<(unsigned)grid, SELL_THREADS, 0, ctx->stream>>>(m, a)
+  switch (variant) {
+    case 1: GSB_SELL(9, 4, 0); break;
+    case 2: GSB_SELL(9, 3, 1); break;
+    case 3: GSB_SELL(27, 1, 1); break;
+    case 4: GSB_SELL(14, 2, 1); break;
+    case 5: GSB_SELL(9, 8, 1); break;
+    case 6: GSB_SELL(27, 2, 1); break;
+    case 7: GSB_SELL(9, 4, 1); break;
+    case 8: GSB_SELL(SELL_U, 1, 0); break;
+    default:
+      // 9 independent loads in flight per lane need ~62 registers; a 32-register build serialises
+      // them and loses 30 % (profiles/sell_variants_r01.json).  The fused-dot mode prefers the
+      // 70-register schedule (its block reduction keeps fewer CTAs busy at the tail).
+      if (MODE == ROW_SPMV_DOT) GSB_SELL(SELL_U, 1, 0);
+      else GSB_SELL(SELL_U, 4, 1);
+      break;
+  }
+#undef GSB_SELL
   launched(ctx);
+}
+
+template <int MODE>
+static void launch_sell(gsb_mat_t A, RowArgs &a) {
+  launch_sell_list<MODE>(A, a, nullptr, (A->n_rows + 31) / 32);
+}
+
+// halo overlap: the interior slices (no ghost column in any of their rows) run while the exchange is
+// in flight on the communication stream; the boundary slices follow once the ghosts have arrived.
+// Same kernel, same per-row arithmetic order -- only the launch is split.
+template <int MODE>
+static void launch_sell_split(gsb_mat_t A, RowArgs &a, gsb_vec_s &xvec) {
+  static_assert(MODE != ROW_SPMV_DOT, "fused dot is not split");
+  const bool skip_comm = A->ctx->opt("split_skip_comm", "0") == "1";  // diagnostics only
+  if (!skip_comm) consistent_begin(xvec, A->plan);
+  launch_sell_list<MODE>(A, a, A->int_slices.p, A->n_int_slices);
+  if (!skip_comm) consistent_end(xvec, A->plan);
+  launch_sell_list<MODE>(A, a, A->bnd_slices.p, A->n_bnd_slices);
+}
+
+static bool use_split(gsb_mat_t A) {
+  gsb_ctx_t ctx = A->ctx;
+  const bool force = ctx->opt("force_split", "0") == "1";  // diagnostics: split kernels on one rank
+  return A->split_ok && A->sell_ok && ((ctx->nranks > 1 && A->plan) || force) && ctx->opt("overlap", "1") == "1" &&
+         ctx->opt("spmv", "auto") != "vector" && ctx->opt("spmv", "auto") != "stream" &&
+         A->n_rows >= (int64_t)std::stoll(ctx->opt("overlap_min_rows", "100000"));
 }
 
 template <int G, int MODE>
@@ -339,10 +413,12 @@ void spmv(gsb_mat_t A, gsb_vec_s &x, gsb_vec_s &y, double alpha, double beta) {
   check_gather(A, x, "mul!");
   GSB_CHECK(y.n_own == A->n_rows, "mul!: y own size != rows of A");
   GSB_CHECK(x.d != y.d, "mul!: x and y alias");
-  consistent(x, A->plan);
+  const bool split = use_split(A);
+  if (!split) consistent(x, A->plan);
   RowArgs a{};
   a.x = x.d; a.y = y.d; a.alpha = alpha; a.beta = beta;
-  launch_rows<ROW_SPMV>(A, a);
+  if (split) launch_sell_split<ROW_SPMV>(A, a, x);
+  else launch_rows<ROW_SPMV>(A, a);
 }
 
 void resid(gsb_mat_t A, gsb_vec_s &x, const gsb_vec_s &b, gsb_vec_s &out) {
@@ -355,10 +431,12 @@ void resid(gsb_mat_t A, gsb_vec_s &x, const gsb_vec_s &b, gsb_vec_s &out) {
   check_gather(A, x, "residual");
   GSB_CHECK(out.n_own == A->n_rows && b.n_own == A->n_rows, "residual: size mismatch");
   GSB_CHECK(x.d != out.d, "residual: x and out alias");
-  consistent(x, A->plan);
+  const bool split = use_split(A);
+  if (!split) consistent(x, A->plan);
   RowArgs a{};
   a.x = x.d; a.b = b.d; a.out = out.d; a.alpha = 1.0;
-  launch_rows<ROW_RESID>(A, a);
+  if (split) launch_sell_split<ROW_RESID>(A, a, x);
+  else launch_rows<ROW_RESID>(A, a);
 }
 
 void sweep(gsb_mat_t A, gsb_vec_s &dx_in, gsb_vec_s &r, const double *invd, double omega, gsb_vec_s &dx_out,
@@ -366,10 +444,12 @@ void sweep(gsb_mat_t A, gsb_vec_s &dx_in, gsb_vec_s &r, const double *invd, doub
   GSB_CHECK(A->nb == 0, "sweep: block matrices not supported");
   check_gather(A, dx_in, "sweep");
   GSB_CHECK(dx_in.d != dx_out.d && dx_in.d != r.d && dx_in.d != xacc.d, "sweep: aliasing");
-  consistent(dx_in, A->plan);
+  const bool split = use_split(A);
+  if (!split) consistent(dx_in, A->plan);
   RowArgs a{};
   a.x = dx_in.d; a.b = r.d; a.out = r.d; a.invd = invd; a.omega = omega; a.dxout = dx_out.d; a.xacc = xacc.d; a.alpha = 1.0;
-  launch_rows<ROW_SWEEP>(A, a);
+  if (split) launch_sell_split<ROW_SWEEP>(A, a, dx_in);
+  else launch_rows<ROW_SWEEP>(A, a);
 }
 
 void spmv_dot(gsb_mat_t A, gsb_vec_s &x, gsb_vec_s &y, const gsb_vec_s &dotv, int slot) {
@@ -392,10 +472,12 @@ void spmv_dot(gsb_mat_t A, gsb_vec_s &x, gsb_vec_s &y, const gsb_vec_s &dotv, in
 void spmv_add(gsb_mat_t A, gsb_vec_s &x, gsb_vec_s &y, gsb_vec_s &xacc) {
   GSB_CHECK(A->nb == 0, "spmv_add: block matrices not supported");
   check_gather(A, x, "mul!");
-  consistent(x, A->plan);
+  const bool split = use_split(A);
+  if (!split) consistent(x, A->plan);
   RowArgs a{};
   a.x = x.d; a.y = y.d; a.xacc = xacc.d; a.alpha = 1.0;
-  launch_rows<ROW_SPMV_ADD>(A, a);
+  if (split) launch_sell_split<ROW_SPMV_ADD>(A, a, x);
+  else launch_rows<ROW_SPMV_ADD>(A, a);
 }
 
 // ---------------------------------------------------------------- dense coarse solver
@@ -552,8 +634,24 @@ int gsb_init(int device, int nranks, int rank, const void *nccl_id, gsb_ctx_t *o
   GSB_CUDA(cudaGetDeviceProperties(&prop, device));
   ctx->num_sms = prop.multiProcessorCount;
   GSB_CHECK(prop.major >= 10, "gsb_init: libgsb200 is built for sm_100a (Blackwell) only");
-  GSB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-  GSB_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+  int prio_lo = 0, prio_hi = 0;
+  GSB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  GSB_CUDA(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_lo));
+  // halo traffic gets the highest priority so that its (tiny) kernels are dispatched ahead of the
+  // tens of thousands of pending CTAs of the row kernel it overlaps with
+  GSB_CUDA(cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, prio_hi));
+  if (const char *env = std::getenv("GSB_OPTIONS")) {  // "key=value,key=value"
+    std::string e(env);
+    size_t pos = 0;
+    while (pos < e.size()) {
+      size_t end = e.find(',', pos);
+      if (end == std::string::npos) end = e.size();
+      const std::string kv = e.substr(pos, end - pos);
+      const size_t eq = kv.find('=');
+      if (eq != std::string::npos) ctx->opts[kv.substr(0, eq)] = kv.substr(eq + 1);
+      pos = end + 1;
+    }
+  }
   GSB_CUDA(cudaEventCreate(&ctx->t0));
   GSB_CUDA(cudaEventCreate(&ctx->t1));
   GSB_CUDA(cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming));
@@ -794,6 +892,27 @@ static void finish_matrix(gsb_mat_s *A, const std::vector<int> &rowptr, const st
       A->sell_ok = true;
       A->h_sell_off = soff;
     }
+  }
+  // interior / boundary slice lists (only for matrices with ghost columns)
+  A->split_ok = false;
+  if (A->sell_ok && A->n_ghost_cols > 0) {
+    std::vector<int> isl, bsl;
+    const int64_t nsl = (A->n_rows + 31) / 32;
+    for (int64_t sl = 0; sl < nsl; ++sl) {
+      bool bnd = false;
+      for (int64_t i = sl * 32; i < std::min<int64_t>(A->n_rows, sl * 32 + 32) && !bnd; ++i) {
+        const int e0 = rowptr[(size_t)i], e1 = rowptr[(size_t)i + 1];
+        bnd = e1 > e0 && col[(size_t)e1 - 1] >= A->n_own_cols;  // columns ascend: ghosts are last
+      }
+      (bnd ? bsl : isl).push_back((int)sl);
+    }
+    A->n_int_slices = (int64_t)isl.size();
+    A->n_bnd_slices = (int64_t)bsl.size();
+    A->int_slices.alloc(std::max<size_t>(1, isl.size()));
+    A->bnd_slices.alloc(std::max<size_t>(1, bsl.size()));
+    if (!isl.empty()) GSB_CUDA(cudaMemcpy(A->int_slices.p, isl.data(), sizeof(int) * isl.size(), cudaMemcpyHostToDevice));
+    if (!bsl.empty()) GSB_CUDA(cudaMemcpy(A->bnd_slices.p, bsl.data(), sizeof(int) * bsl.size(), cudaMemcpyHostToDevice));
+    A->split_ok = true;
   }
   // persistent-CTA row partition balanced by nnz
   const int rows_per_step = ST_THREADS / A->G;

@@ -82,6 +82,10 @@ struct gsb_ctx_s {
   double *h_scal = nullptr;  // pinned host mirror for read-backs
   std::map<std::string, std::string> opts;
   std::string err;
+  // a caller that already knows ||b|| on the host (CG knows ||r||, GMRES knows ||V_j|| = 1) tells the
+  // next inner solve, so that a maxiter=1 GMG preconditioner need not synchronise to decide `done`
+  const double *hint_vec = nullptr;
+  double hint_norm = 0.0;
   // optional per-launch profiling of the row kernels (bench.py's roofline numbers)
   struct ProfRec { int mode; int stream; int64_t nrows, nnz; cudaEvent_t e0, e1; };
   bool profiling = false;
@@ -138,6 +142,11 @@ struct gsb_mat_s {
   gsb::DevBuf<int> sell_off, sell_col;
   std::vector<int> h_sell_off;
   gsb::DevBuf<double> sell_val;
+  // halo overlap: slices whose rows touch no ghost column ("interior") run while the exchange is in
+  // flight, the remaining ("boundary") slices after it
+  bool split_ok = false;
+  int64_t n_int_slices = 0, n_bnd_slices = 0;
+  gsb::DevBuf<int> int_slices, bnd_slices;
   // block matrix (acts on concatenated vectors)
   int nb = 0;
   std::vector<gsb_mat_t> blocks;  // row-major nb*nb, may contain nullptr
@@ -191,5 +200,6 @@ struct gsb_solver_s {
   virtual void update(gsb_mat_t A) { (void)A; }       // numerical_setup!(ns,A)
   virtual const char *name() const = 0;
   virtual gsb_mat_t matrix() { return nullptr; }       // the system matrix, when the solver has one
+  virtual void finish() {}                             // resolve a deferred (device-resident) log
   std::unique_ptr<gsb_vec_s> host_x, host_b;           // staging for gsb_solve_host
 };

@@ -200,6 +200,8 @@ __device__ __forceinline__ int ldg_stream_s32(const int *p) {
 }
 
 struct SellArgs {
+  const int *slice_list;  // optional indirection: the slices this launch processes (nullptr = all)
+  int64_t n_list;         // number of slices this launch processes
   const int *rowptr;      // CSR row pointers (row lengths)
   const int *slice_off;   // per slice: offset of the slice in units of 32 entries; nslices+1 entries
   const int *col;         // padded, column-major per slice
@@ -207,15 +209,15 @@ struct SellArgs {
   int64_t nrows;
 };
 
-template <int MODE, int THREADS, int U>
-__global__ void __launch_bounds__(THREADS) csr_sell_kernel(SellArgs m, RowArgs a) {
+template <int MODE, int THREADS, int U, int MINB = 1, int STYLE = 0>
+__global__ void __launch_bounds__(THREADS, MINB) csr_sell_kernel(SellArgs m, RowArgs a) {
   __shared__ double red_smem[THREADS / 32];
-  const int64_t row = (int64_t)blockIdx.x * THREADS + threadIdx.x;
+  const int64_t widx = ((int64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;  // one warp per slice
   const int lane = threadIdx.x & 31;
-  const int64_t slice = row >> 5;
-  const int64_t nslices = (m.nrows + 31) >> 5;
   double acc = 0.0;
-  if (slice < nslices) {  // warp-uniform
+  if (widx < m.n_list) {  // warp-uniform
+    const int64_t slice = m.slice_list ? (int64_t)m.slice_list[widx] : widx;
+    const int64_t row = (slice << 5) + lane;
     const bool valid = row < m.nrows;
     const int so0 = m.slice_off[slice], so1 = m.slice_off[slice + 1];
     const int width = so1 - so0;  // entries per row in this slice (warp-uniform)
@@ -235,13 +237,27 @@ __global__ void __launch_bounds__(THREADS) csr_sell_kernel(SellArgs m, RowArgs a
     for (; k + U <= width; k += U) {
       int cc[U];
       double vv[U], xv[U];
+      if (STYLE == 0) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        cc[u] = ldg_stream_s32(cp + (size_t)(k + u) * 32);
-        vv[u] = ldg_stream_f64(vp + (size_t)(k + u) * 32);
+        for (int u = 0; u < U; ++u) {
+          cc[u] = ldg_stream_s32(cp + (size_t)(k + u) * 32);
+          vv[u] = ldg_stream_f64(vp + (size_t)(k + u) * 32);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) xv[u] = __ldg(a.x + cc[u]);
+      } else {
+        // burst order: all column ids, then all values (two contiguous bursts per warp), then the gathers
+#pragma unroll
+        for (int u = 0; u < U; ++u) cc[u] = ldg_stream_s32(cp + (size_t)(k + u) * 32);
+#pragma unroll
+        for (int u = 0; u < U; ++u) vv[u] = ldg_stream_f64(vp + (size_t)(k + u) * 32);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          double t;
+          asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(t) : "l"(a.x + cc[u]));
+          xv[u] = t;
+        }
       }
-#pragma unroll
-      for (int u = 0; u < U; ++u) xv[u] = __ldg(a.x + cc[u]);
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (k + u < len) {

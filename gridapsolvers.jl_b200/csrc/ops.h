@@ -19,6 +19,10 @@ void ew_mul_raw(gsb_vec_s &z, const double *dvec, const gsb_vec_s &x);
 void dot(const gsb_vec_s &a, const gsb_vec_s &b, int slot);
 // consistent!(v): owner -> ghost update through the plan (no-op for nranks == 1 / no ghosts)
 void consistent(gsb_vec_s &v, gsb_plan_t plan);
+// same exchange on the communication stream; returns immediately, `consistent_end` makes the compute
+// stream wait for the ghosts
+void consistent_begin(gsb_vec_s &v, gsb_plan_t plan);
+void consistent_end(gsb_vec_s &v, gsb_plan_t plan);
 
 // row kernels (halo exchange of the gathered vector included)
 void spmv(gsb_mat_t A, gsb_vec_s &x, gsb_vec_s &y, double alpha, double beta);          // mul!(y,A,x,alpha,beta)

@@ -53,8 +53,9 @@ def main():
     gsb.consistent_(x, dh.plans[0])
     assert np.array_equal(x.get_local(), xg[gid]), "ghost values differ from owners'"
 
-    # 2. SpMV
-    for kern in ("sell", "stream", "vector"):
+    # 2. SpMV (the "auto" runs use the own/ghost split with the halo exchange overlapped on a second stream)
+    ctx.set_option("overlap_min_rows", os.environ.get("MGPU_OVERLAP_MIN_ROWS", "1"))
+    for kern in ("auto", "sell", "stream", "vector"):
         ctx.set_option("spmv", kern)
         y = gsb.allocate_in_range(A)
         x.set(xg[gid[: lp.n_own]])
@@ -63,6 +64,12 @@ def main():
         yo = np.zeros(lp.n_own)
         ola.mul(yo, Ao, xg[gid])
         assert np.array_equal(y.get(), yo), f"distributed SpMV ({kern}) not bit-identical to the own-first CSR order"
+        if kern == "auto":  # 5-arg form and repeated exchanges through the split path
+            y.set(yo)
+            gsb.mul_(y, A, x, -0.5, 1.0)
+            y2 = yo.copy()
+            ola.mul5(y2, Ao, xg[gid], -0.5, 1.0)
+            assert np.array_equal(y.get(), y2)
     ctx.set_option("spmv", "auto")
     d = gsb.dot(x, x)
     assert abs(d - float(xg @ xg)) <= 1e-13 * float(xg @ xg)

@@ -15,11 +15,12 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_distributed_parity(world):
+@pytest.mark.parametrize("world,cells", [(2, 16), (2, 64), (4, 16), (8, 16)])
+def test_distributed_parity(world, cells):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
-    port = 29600 + world
+    port = 29600 + world + cells
+    os.environ["MGPU_CELLS"] = str(cells)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
