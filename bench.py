@@ -33,7 +33,8 @@ if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
     os.environ["NCCL_DEBUG"] = "WARN"
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
-PARTS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+# part grids (px,py,pz): split the slowest-varying directions first so that halo faces are contiguous planes
+PARTS = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}
 RTOL, ATOL, MAXITER = 1e-8, 1e-14, 100
 
 
@@ -289,25 +290,30 @@ def main():
     peak, peak_src = peaks()
 
     # roofline of the dominant kernel: the fused Jacobi-Richardson sweep on the finest level
-    def algo_bytes(mode, nrows, nnz):
-        per_row = {"spmv": 20, "spmv_dot": 28, "residual": 28, "sweep": 44, "spmv_add": 36}[mode]
-        return 12 * nnz + per_row * nrows
+    def algo_bytes(mode, nrows, nnz, impl=""):
+        per_row = {"spmv": 20, "spmv_dot": 28, "residual": 28, "sweep": 44, "spmv_add": 36, "sweeps_pipelined": 44}[mode]
+        nsweeps = int(impl.rsplit("S", 1)[1]) if mode == "sweeps_pipelined" else 1  # S sweeps per launch
+        return nsweeps * (12 * nnz + per_row * nrows)
 
     kernels = []
     for p in res.get("prof", []):
         t = p["total_ms"] / p["count"] * 1e-3
         kernels.append({"kernel": p["mode"], "impl": p["impl"], "rows": p["nrows"], "nnz": p["nnz"],
                         "launches": p["count"], "avg_us": round(t * 1e6, 2),
-                        "GBps": round(algo_bytes(p["mode"], p["nrows"], p["nnz"]) / t / 1e9, 1),
+                        "GBps": round(algo_bytes(p["mode"], p["nrows"], p["nnz"], p["impl"]) / t / 1e9, 1),
                         "share_of_solve": round(p["total_ms"] / res["ms"], 4)})
     kernels.sort(key=lambda k: -k["share_of_solve"])
-    top = next((k for k in kernels if k["kernel"] == "sweep" and k["rows"] == res["rows"][0]), kernels[0] if kernels else None)
+    top = next((k for k in kernels if k["kernel"] in ("sweep", "sweeps_pipelined") and k["rows"] == res["rows"][0]), kernels[0] if kernels else None)
     roofline = None
     if top:
-        roofline = {"bound": "hbm", "kernel": "csr_sell_kernel<sweep> level 1 (fused Jacobi-Richardson sweep, SELL-32)",
+        pipelined = top["kernel"] == "sweeps_pipelined"
+        nsw = int(top["impl"].rsplit("S", 1)[1]) if pipelined else 1
+        roofline = {"bound": "hbm", "kernel": ("sell_pipe_kernel level 1 (%d fused Jacobi-Richardson sweeps per launch, matrix re-read from L2)" % nsw) if pipelined
+                    else "csr_sell_kernel<sweep> level 1 (fused Jacobi-Richardson sweep, SELL-32)",
                     "achieved": top["GBps"], "peak": peak, "unit": "GB/s", "frac": round(top["GBps"] / peak, 4),
                     "frac_of_nominal_8TBs": round(top["GBps"] / 8000.0, 4), "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": algo_bytes("sweep", top["rows"], top["nnz"]),
+                    "algorithmic_bytes_per_launch": algo_bytes(top["kernel"], top["rows"], top["nnz"], top["impl"]),
+                    "sweeps_per_launch": nsw,
                     "avg_launch_us": top["avg_us"], "traffic": None}
         tfile = os.path.join(ROOT, "profiles", "traffic_r01.json")
         if os.path.exists(tfile):

@@ -184,6 +184,22 @@ static bool plan_active(gsb_vec_s &v, gsb_plan_t plan) {
 static void exchange_on(gsb_vec_s &v, gsb_plan_t plan, cudaStream_t st) {
   gsb_ctx_t ctx = v.ctx;
   const int64_t nsnd = plan->snd_ptrs.back(), nrcv = plan->rcv_ptrs.back();
+  if (plan->p2p) {
+    plan->seq += 1;
+    const int par = (int)(plan->seq & 1ull);
+    P2PPush ps{nsnd, plan->snd_ids.p, plan->snd_nbr.p, plan->snd_ptrs_dev.p, plan->peer_buf[par].p, plan->peer_flag.p,
+               (int)plan->nbr_snd.size(), plan->seq, plan->ticket.p};
+    const int g1 = (int)std::max<int64_t>(1, std::min<int64_t>((nsnd + 255) / 256, 2 * ctx->num_sms));
+    p2p_push_kernel<<<g1, 256, 0, st>>>(ps, v.d);
+    launched(ctx);
+    const double *rb = (const double *)((char *)plan->block + plan->flag_bytes) + (size_t)par * (size_t)std::max<int64_t>(nrcv, 1);
+    P2PWait pw{(int)plan->nbr_rcv.size(), plan->nbr_rcv_dev.p, (const unsigned long long *)plan->block, plan->seq, nrcv,
+               plan->rcv_ids.p, rb};
+    const int g2 = (int)std::max<int64_t>(1, std::min<int64_t>((nrcv + 255) / 256, 2 * ctx->num_sms));
+    p2p_wait_unpack_kernel<<<g2, 256, 0, st>>>(pw, v.d);
+    launched(ctx);
+    return;
+  }
   if (nsnd) {
     int grid = (int)std::min<int64_t>((nsnd + 255) / 256, 1024);
     pack_kernel<<<grid, 256, 0, st>>>(nsnd, plan->snd_ids.p, v.d, plan->snd_buf.p);
@@ -450,6 +466,49 @@ void sweep(gsb_mat_t A, gsb_vec_s &dx_in, gsb_vec_s &r, const double *invd, doub
   a.x = dx_in.d; a.b = r.d; a.out = r.d; a.invd = invd; a.omega = omega; a.dxout = dx_out.d; a.xacc = xacc.d; a.alpha = 1.0;
   if (split) launch_sell_split<ROW_SWEEP>(A, a, dx_in);
   else launch_rows<ROW_SWEEP>(A, a);
+}
+
+constexpr int PIPE_THREADS = 256;
+bool sweeps_pipelined(gsb_mat_t A, const double *invd, double omega, int niter, gsb_vec_s &r, gsb_vec_s &x,
+                      gsb_vec_s &dxa, gsb_vec_s &dxb) {
+  gsb_ctx_t ctx = A->ctx;
+  const int smax = std::stoi(ctx->opt("pipe_stages", "1"));  // opt-in: see DESIGN.md section 5 (no net gain measured)
+  if (smax < 2 || niter < 2 || !A->sell_ok || A->nb > 0 || A->n_ghost_cols > 0 || A->n_rows != A->n_own_cols) return false;
+  const int grid = ctx->num_sms * std::min(4, std::max(1, std::stoi(ctx->opt("pipe_ctas_per_sm", "4"))));
+  const int nchunks = (int)((A->n_rows + PIPE_THREADS - 1) / PIPE_THREADS);
+  if (nchunks < (int)std::stoll(ctx->opt("pipe_min_chunks", std::to_string(4 * grid)))) return false;
+  const int reach = (int)(A->bw_rows / PIPE_THREADS) + 1;
+  if (A->pipe_ctr.n == 0) {
+    A->pipe_ctr.alloc(2);
+    A->pipe_prefix.alloc(32);
+    A->pipe_done.alloc((size_t)32 * (size_t)nchunks);
+    GSB_CUDA(cudaMemsetAsync(A->pipe_ctr.p, 0, 2 * sizeof(unsigned int), ctx->stream));
+    GSB_CUDA(cudaMemsetAsync(A->pipe_prefix.p, 0, 32 * sizeof(int), ctx->stream));
+    GSB_CUDA(cudaMemsetAsync(A->pipe_done.p, 0, sizeof(int) * 32 * (size_t)nchunks, ctx->stream));
+  }
+  int k0 = 1;
+  while (k0 <= niter) {
+    const int S = std::min(std::min(smax, 32), niter - k0 + 1);
+    PipeArgs p{};
+    p.m = SellArgs{nullptr, (A->n_rows + 31) / 32, A->rowptr.p, A->sell_off.p, A->sell_col.p, A->sell_val.p, A->n_rows};
+    p.r = r.d; p.x = x.d; p.invd = invd; p.dxbuf[0] = dxa.d; p.dxbuf[1] = dxb.d; p.omega = omega;
+    p.k0 = k0; p.S = S; p.niter = niter; p.nchunks = nchunks; p.reach = reach;
+    p.lag = reach + (grid + S - 1) / S + std::stoi(ctx->opt("pipe_lag_margin", "64"));
+    p.ticket = A->pipe_ctr.p; p.exited = A->pipe_ctr.p + 1; p.prefix = A->pipe_prefix.p; p.done = A->pipe_done.p;
+    p.epoch = ++A->pipe_epoch;
+    p.l2_hints = ctx->opt("pipe_l2_hints", "1") == "1";
+    gsb_ctx_s::ProfRec rec{};
+    if (ctx->profiling) {
+      rec.mode = 5; rec.stream = 100 + S; rec.nrows = A->n_rows; rec.nnz = A->nnz;
+      GSB_CUDA(cudaEventCreate(&rec.e0)); GSB_CUDA(cudaEventCreate(&rec.e1));
+      GSB_CUDA(cudaEventRecord(rec.e0, ctx->stream));
+    }
+    sell_pipe_kernel<PIPE_THREADS, SELL_U><<<grid, PIPE_THREADS, 0, ctx->stream>>>(p);
+    launched(ctx);
+    if (ctx->profiling) { GSB_CUDA(cudaEventRecord(rec.e1, ctx->stream)); ctx->prof.push_back(rec); }
+    k0 += S;
+  }
+  return true;
 }
 
 void spmv_dot(gsb_mat_t A, gsb_vec_s &x, gsb_vec_s &y, const gsb_vec_s &dotv, int slot) {
@@ -789,6 +848,86 @@ int gsb_set_option(gsb_ctx_t ctx, const char *key, const char *value) {
 }
 
 // ---------------------------------------------------------------- plan
+gsb_plan_s::~gsb_plan_s() {
+  for (void *b : peer_base)
+    if (b) cudaIpcCloseMemHandle(b);
+  if (block) cudaFree(block);
+}
+
+// COLLECTIVE over all ranks (every rank creates its plans in the same order): exchanges the CUDA-IPC
+// handles of the receive blocks and the slot offsets, and maps the send neighbours' blocks.
+static void setup_p2p(gsb_plan_s *p) {
+  gsb_ctx_t ctx = p->ctx;
+  const int R = ctx->nranks, me = ctx->rank;
+  const int64_t nsnd = p->snd_ptrs.back(), nrcv = p->rcv_ptrs.back();
+  // all ranks must be able to map each other (same node, NVLink / PCIe P2P)
+  p->flag_bytes = ((size_t)R * sizeof(unsigned long long) + 255) & ~(size_t)255;
+  const size_t bytes = p->flag_bytes + 2 * sizeof(double) * (size_t)std::max<int64_t>(nrcv, 1);
+  GSB_CUDA(cudaMalloc(&p->block, bytes));
+  GSB_CUDA(cudaMemset(p->block, 0, bytes));
+  cudaIpcMemHandle_t h;
+  GSB_CUDA(cudaIpcGetMemHandle(&h, p->block));
+  // record per rank: [64 B handle | nrcv | off_from[0..R-1]]
+  const size_t rec = 64 + sizeof(int64_t) * (size_t)(1 + R);
+  std::vector<char> mine(rec, 0), all(rec * (size_t)R, 0);
+  std::memcpy(mine.data(), &h, sizeof(h));
+  int64_t *meta = (int64_t *)(mine.data() + 64);
+  meta[0] = nrcv;
+  for (int q = 0; q < R; ++q) meta[1 + q] = -1;
+  for (size_t k = 0; k < p->nbr_rcv.size(); ++k) meta[1 + p->nbr_rcv[k]] = p->rcv_ptrs[k];
+  DevBuf<char> dmine(rec), dall(rec * (size_t)R);
+  GSB_CUDA(cudaMemcpy(dmine.p, mine.data(), rec, cudaMemcpyHostToDevice));
+  GSB_NCCL(ncclAllGather(dmine.p, dall.p, rec, ncclChar, ctx->comm, ctx->stream));
+  GSB_CUDA(cudaStreamSynchronize(ctx->stream));
+  GSB_CUDA(cudaMemcpy(all.data(), dall.p, all.size(), cudaMemcpyDeviceToHost));
+  const size_t nn = p->nbr_snd.size();
+  std::vector<double *> pb0(std::max<size_t>(nn, 1), nullptr), pb1(std::max<size_t>(nn, 1), nullptr);
+  std::vector<unsigned long long *> pf(std::max<size_t>(nn, 1), nullptr);
+  p->peer_base.assign(nn, nullptr);
+  for (size_t k = 0; k < nn; ++k) {
+    const int q = p->nbr_snd[k];
+    const char *rq = all.data() + rec * (size_t)q;
+    cudaIpcMemHandle_t hq;
+    std::memcpy(&hq, rq, sizeof(hq));
+    const int64_t *mq = (const int64_t *)(rq + 64);
+    const int64_t nrcv_q = mq[0], off = mq[1 + me];
+    GSB_CHECK(off >= 0, "p2p plan: neighbour " + std::to_string(q) + " does not expect data from rank " + std::to_string(me));
+    void *base = nullptr;
+    GSB_CUDA(cudaIpcOpenMemHandle(&base, hq, cudaIpcMemLazyEnablePeerAccess));
+    p->peer_base[k] = base;
+    const size_t fb = ((size_t)R * sizeof(unsigned long long) + 255) & ~(size_t)255;
+    double *buf0 = (double *)((char *)base + fb);
+    pb0[k] = buf0 + off;
+    pb1[k] = buf0 + (size_t)std::max<int64_t>(nrcv_q, 1) + off;
+    pf[k] = (unsigned long long *)base + me;
+  }
+  // parity 1 is used by the first exchange (seq = 1)
+  p->peer_buf[0].alloc(pb0.size());
+  p->peer_buf[1].alloc(pb1.size());
+  p->peer_flag.alloc(pf.size());
+  GSB_CUDA(cudaMemcpy(p->peer_buf[0].p, pb0.data(), sizeof(double *) * pb0.size(), cudaMemcpyHostToDevice));
+  GSB_CUDA(cudaMemcpy(p->peer_buf[1].p, pb1.data(), sizeof(double *) * pb1.size(), cudaMemcpyHostToDevice));
+  GSB_CUDA(cudaMemcpy(p->peer_flag.p, pf.data(), sizeof(unsigned long long *) * pf.size(), cudaMemcpyHostToDevice));
+  std::vector<int> snbr((size_t)std::max<int64_t>(nsnd, 1), 0);
+  for (size_t k = 0; k < nn; ++k)
+    for (int64_t i = p->snd_ptrs[k]; i < p->snd_ptrs[k + 1]; ++i) snbr[(size_t)i] = (int)k;
+  p->snd_nbr.alloc(snbr.size());
+  GSB_CUDA(cudaMemcpy(p->snd_nbr.p, snbr.data(), sizeof(int) * snbr.size(), cudaMemcpyHostToDevice));
+  p->snd_ptrs_dev.alloc(p->snd_ptrs.size());
+  GSB_CUDA(cudaMemcpy(p->snd_ptrs_dev.p, p->snd_ptrs.data(), sizeof(int64_t) * p->snd_ptrs.size(), cudaMemcpyHostToDevice));
+  p->nbr_rcv_dev.alloc(std::max<size_t>(1, p->nbr_rcv.size()));
+  if (!p->nbr_rcv.empty())
+    GSB_CUDA(cudaMemcpy(p->nbr_rcv_dev.p, p->nbr_rcv.data(), sizeof(int) * p->nbr_rcv.size(), cudaMemcpyHostToDevice));
+  p->ticket.alloc(1);
+  GSB_CUDA(cudaMemset(p->ticket.p, 0, sizeof(unsigned int)));
+  // nobody may push before every rank has zeroed its flags and mapped its peers
+  DevBuf<double> tok(1);
+  GSB_CUDA(cudaMemset(tok.p, 0, sizeof(double)));
+  GSB_NCCL(ncclAllReduce(tok.p, tok.p, 1, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+  GSB_CUDA(cudaStreamSynchronize(ctx->stream));
+  p->p2p = true;
+}
+
 int gsb_plan_create(gsb_ctx_t ctx, int64_t n_own, int64_t n_ghost, int n_nbr_snd, const int32_t *nbr_snd,
                     const int64_t *snd_ptrs, const int64_t *snd_local_ids, int n_nbr_rcv, const int32_t *nbr_rcv,
                     const int64_t *rcv_ptrs, const int64_t *rcv_local_ids, int index_base, gsb_plan_t *out) {
@@ -820,6 +959,7 @@ int gsb_plan_create(gsb_ctx_t ctx, int64_t n_own, int64_t n_ghost, int n_nbr_snd
   p->rcv_buf.alloc(std::max<size_t>(1, r.size()));
   if (nsnd) GSB_CUDA(cudaMemcpy(p->snd_ids.p, s.data(), sizeof(int) * s.size(), cudaMemcpyHostToDevice));
   if (nrcv) GSB_CUDA(cudaMemcpy(p->rcv_ids.p, r.data(), sizeof(int) * r.size(), cudaMemcpyHostToDevice));
+  if (ctx->nranks > 1 && ctx->opt("p2p", "1") == "1") setup_p2p(p.get());
   *out = p.release();
   API_END(ctx)
 }
@@ -853,6 +993,13 @@ static void finish_matrix(gsb_mat_s *A, const std::vector<int> &rowptr, const st
   int mx = 0;
   for (int64_t i = 0; i < A->n_rows; ++i) mx = std::max(mx, rowptr[(size_t)i + 1] - rowptr[(size_t)i]);
   A->max_row_nnz = mx;
+  {
+    int64_t bw = 0;
+    for (int64_t i = 0; i < A->n_rows; ++i)
+      for (int e = rowptr[(size_t)i]; e < rowptr[(size_t)i + 1]; ++e)
+        if (col[(size_t)e] < A->n_own_cols) bw = std::max<int64_t>(bw, std::llabs((int64_t)col[(size_t)e] - i));
+    A->bw_rows = bw;
+  }
   const double avg = A->n_rows ? (double)A->nnz / (double)A->n_rows : 0.0;
   A->G = avg <= 48.0 ? 1 : (avg <= 160.0 ? 4 : 16);
   A->stream_ok = mx <= ST_SPAN_MAX && A->n_rows > 0;
@@ -870,7 +1017,10 @@ static void finish_matrix(gsb_mat_s *A, const std::vector<int> &rowptr, const st
       soff[(size_t)sl + 1] = (int)tot;
     }
     const int64_t entries = tot * 32;
-    if (tot < INT32_MAX && (double)entries <= 1.25 * (double)std::max<int64_t>(A->nnz, 1) + 4096) {
+    // padding budget: 25 %; very short rows (prolongations: 1/2/4/8 entries) may pad up to 3x -- a padded
+    // coalesced slice still beats the row-pointer-chasing CSR kernels there
+    const double pad_ok = (avg <= 8.0) ? 3.0 : 1.25;
+    if (tot < INT32_MAX && (double)entries <= pad_ok * (double)std::max<int64_t>(A->nnz, 1) + 4096) {
       std::vector<int> sc((size_t)std::max<int64_t>(entries, 1), 0);
       std::vector<double> sv((size_t)std::max<int64_t>(entries, 1), 0.0);
 #pragma omp parallel for schedule(static)

@@ -109,6 +109,18 @@ struct gsb_plan_s {
   gsb::DevBuf<int> snd_ids, rcv_ids;        // 0-based local ids
   gsb::DevBuf<double> snd_buf, rcv_buf;
   bool rcv_contiguous = false;  // ghosts of each neighbour form one ascending run -> no unpack
+  // NVLink peer-memory exchange (CUDA IPC); see kernels.cuh p2p_push_kernel
+  bool p2p = false;
+  unsigned long long seq = 0;
+  void *block = nullptr;                 // [flags: nranks u64 | buf parity 0 | buf parity 1]
+  size_t flag_bytes = 0;
+  std::vector<void *> peer_base;         // opened IPC mappings of the send neighbours' blocks
+  gsb::DevBuf<int> snd_nbr, nbr_rcv_dev;
+  gsb::DevBuf<int64_t> snd_ptrs_dev;
+  gsb::DevBuf<double *> peer_buf[2];
+  gsb::DevBuf<unsigned long long *> peer_flag;
+  gsb::DevBuf<unsigned int> ticket;
+  ~gsb_plan_s();
 };
 
 struct gsb_vec_s {
@@ -142,6 +154,11 @@ struct gsb_mat_s {
   gsb::DevBuf<int> sell_off, sell_col;
   std::vector<int> h_sell_off;
   gsb::DevBuf<double> sell_val;
+  // L2-pipelined multi-sweep smoother (kernels.cuh sell_pipe_kernel)
+  int64_t bw_rows = 0;  // max |col - row| over the own columns
+  gsb::DevBuf<unsigned int> pipe_ctr;  // [ticket, exited]
+  gsb::DevBuf<int> pipe_prefix, pipe_done;
+  int pipe_epoch = 0;
   // halo overlap: slices whose rows touch no ghost column ("interior") run while the exchange is in
   // flight, the remaining ("boundary") slices after it
   bool split_ok = false;

@@ -285,6 +285,190 @@ __global__ void __launch_bounds__(THREADS, MINB) csr_sell_kernel(SellArgs m, Row
 }
 
 // ------------------------------------------------------------------------------------------
+// L2-pipelined Jacobi-Richardson sweeps: S consecutive sweeps of the smoother in ONE launch, so that
+// the matrix is streamed from HBM once and re-read S-1 times from the 126 MB L2.
+//
+// Work item = (stage j, chunk c of 256 rows).  Items are handed out in the order
+//     tau = 0,1,2,... ; j = 0..S-1 ; c = tau - j*LAG
+// i.e. stage j trails stage j-1 by LAG chunks.  Stage j of chunk c gathers dx produced by stage j-1
+// on chunks [c-reach, c+reach] (reach = matrix bandwidth in chunks) and overwrites the dx buffer that
+// stage j-1 itself gathered from, so it may start only when stage j-1 has completed every chunk up
+// to c+reach: one monotone counter per stage (`prefix[j]` = number of leading chunks completed)
+// carries both the RAW and the WAR dependency.  LAG > reach + (items in flight)/S makes the wait
+// almost never spin, and every dependency of an item has a smaller ticket, so persistent CTAs that
+// take tickets in order can never deadlock.  Arithmetic per row is exactly that of ROW_SWEEP /
+// ROW_RESID (same order, same roundings): the result is bit-identical to S separate launches.
+// Vectors written inside the kernel are read with ld.global.cg (L2) -- L1 is not coherent.
+// matrix loads with an L2 cache-policy hint (createpolicy): evict_last while a later pipeline stage will
+// re-read the line, evict_first on its final use
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ double ldg_hint_f64(const double *p, uint64_t pol) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ int ldg_hint_s32(const int *p, uint64_t pol) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+
+struct PipeArgs {
+  SellArgs m;
+  double *r, *x;
+  const double *invd;
+  double *dxbuf[2];
+  double omega;
+  int k0;        // global index (1-based) of the sweep stage 0 performs
+  int S;         // stages in this launch
+  int niter;     // total sweeps of the smoother application: sweep niter only updates r
+  int nchunks, lag, reach;
+  unsigned int *ticket;  // work counter (zero at launch; reset by the last CTA)
+  unsigned int *exited;
+  int *prefix;   // S counters, zero at launch
+  int *done;     // S * nchunks flags, compared against epoch
+  int epoch;
+  int l2_hints;  // use L2 eviction-priority hints on the matrix stream
+};
+
+template <int THREADS, int U>
+__global__ void __launch_bounds__(THREADS, 4) sell_pipe_kernel(PipeArgs p) {
+  __shared__ unsigned int s_t[2];
+  __shared__ int s_lo;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned int total = (unsigned int)(p.nchunks + (p.S - 1) * p.lag) * (unsigned int)p.S;
+  if (threadIdx.x == 0) s_t[0] = atomicAdd(p.ticket, 1u);
+  const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
+  int it = 0;
+  for (;; ++it) {
+    __syncthreads();
+    const unsigned int t = s_t[it & 1];
+    if (t >= total) break;
+    // take the next ticket now: its latency overlaps this item's work
+    if (threadIdx.x == 0) s_t[(it + 1) & 1] = atomicAdd(p.ticket, 1u);
+    const int tau = (int)(t / (unsigned int)p.S), j = (int)(t % (unsigned int)p.S);
+    const int c = tau - j * p.lag;
+    if (c < 0 || c >= p.nchunks) continue;
+    if (j > 0) {
+      // stage j-1 must have completed every chunk below `need`: start from the published lower
+      // bound and check the completion flags of the remaining chunks with the whole CTA
+      const int need = min(p.nchunks, c + p.reach + 1);
+      int *pf = p.prefix + (j - 1);
+      const int *dn = p.done + (size_t)(j - 1) * p.nchunks;
+      const long long t0 = clock64();
+      for (;;) {
+        // one thread reads the lower bound: every thread must scan from the SAME value, or the
+        // strided scans would leave holes
+        if (threadIdx.x == 0) {
+          int v;
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(pf) : "memory");
+          s_lo = v;
+        }
+        __syncthreads();
+        const int lo = s_lo;
+        bool ok = true;
+        for (int q = lo + (int)threadIdx.x; q < need; q += THREADS) {
+          int fl;
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(fl) : "l"(dn + q) : "memory");
+          ok = ok && (fl == p.epoch);
+        }
+        if (__syncthreads_and(ok)) {
+          if (threadIdx.x == 0 && need > lo) atomicMax(pf, need);
+          break;
+        }
+        if (clock64() - t0 > 20000000000LL) __trap();
+        __nanosleep(200);
+      }
+    }
+    // a later stage re-reads this chunk's matrix rows -> ask L2 to keep them; final use -> evict first
+    const uint64_t pol = (j + 1 < p.S) ? pol_keep : pol_drop;
+    const int k = p.k0 + j;            // sweep index
+    const bool last = (k == p.niter);  // the final sweep only updates the residual
+    const double *xin = p.dxbuf[(k - 1) & 1];
+    double *dxout = p.dxbuf[k & 1];
+    const int64_t slice = (int64_t)c * (THREADS / 32) + warp;
+    const int64_t nslices = (p.m.nrows + 31) >> 5;
+    if (slice < nslices) {
+      const int64_t row = (slice << 5) + lane;
+      const bool valid = row < p.m.nrows;
+      const int so0 = p.m.slice_off[slice], so1 = p.m.slice_off[slice + 1];
+      const int width = so1 - so0;
+      int len = 0;
+      double rb = 0.0, idg = 0.0, xa = 0.0, s = 0.0;
+      if (valid) {
+        len = p.m.rowptr[row + 1] - p.m.rowptr[row];
+        rb = __ldcg(p.r + row);
+        if (!last) { idg = __ldg(p.invd + row); xa = __ldcg(p.x + row); }
+      }
+      const size_t base = ((size_t)so0 << 5) + lane;
+      const int *cp = p.m.col + base;
+      const double *vp = p.m.val + base;
+      int kk = 0;
+      for (; kk + U <= width; kk += U) {
+        int cc[U];
+        double vv[U], xv[U];
+        if (p.l2_hints) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) cc[u] = ldg_hint_s32(cp + (size_t)(kk + u) * 32, pol);
+#pragma unroll
+          for (int u = 0; u < U; ++u) vv[u] = ldg_hint_f64(vp + (size_t)(kk + u) * 32, pol);
+        } else {
+#pragma unroll
+          for (int u = 0; u < U; ++u) cc[u] = ldg_stream_s32(cp + (size_t)(kk + u) * 32);
+#pragma unroll
+          for (int u = 0; u < U; ++u) vv[u] = ldg_stream_f64(vp + (size_t)(kk + u) * 32);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) xv[u] = __ldcg(xin + cc[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (kk + u < len) s = __dadd_rn(s, __dmul_rn(vv[u], xv[u]));
+      }
+      for (; kk < width; ++kk) {
+        const int cidx = ldg_stream_s32(cp + (size_t)kk * 32);
+        const double v = ldg_stream_f64(vp + (size_t)kk * 32);
+        const double tx = __ldcg(xin + cidx);
+        if (kk < len) s = __dadd_rn(s, __dmul_rn(v, tx));
+      }
+      if (valid) {
+        const double rn = __dsub_rn(rb, s);
+        p.r[row] = rn;
+        if (!last) {
+          const double d = __dmul_rn(p.omega, __dmul_rn(idg, rn));
+          dxout[row] = d;
+          p.x[row] = __dadd_rn(xa, d);
+        }
+      }
+    }
+    // publish: every thread's stores first (fence), then this chunk's completion flag
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0)
+      asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.done + (size_t)j * p.nchunks + c), "r"(p.epoch) : "memory");
+  }
+  // the last CTA to leave resets the counters for the next launch
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(p.exited, 1u) == gridDim.x - 1) {
+      *p.ticket = 0u;
+      *p.exited = 0u;
+      for (int j = 0; j < p.S; ++j) p.prefix[j] = 0;
+      __threadfence();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + TMA 1-D bulk copy (cp.async.bulk, SASS: UBLKCP)
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -638,6 +822,72 @@ __global__ void pack_kernel(int64_t n, const int *__restrict__ ids, const double
 }
 __global__ void unpack_kernel(int64_t n, const int *__restrict__ ids, const double *__restrict__ buf, double *__restrict__ v) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[ids[i]] = buf[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// halo exchange over NVLink peer memory (one process per GPU, buffers shared with CUDA IPC):
+//   push kernel  : gathers the own entries each neighbour needs and stores them straight into that
+//                  neighbour's receive buffer (peer addresses -> NVLink/NVSwitch writes); the last
+//                  block to finish publishes this exchange's sequence number in every neighbour's
+//                  flag word (system-scope release)
+//   wait/unpack  : spins on the local flag words until every neighbour has published the sequence
+//                  number (system-scope acquire), then scatters the receive buffer into the ghost tail
+// Receive buffers are double-buffered by the parity of the sequence number: a sender can only run one
+// exchange ahead of a receiver (it needs the receiver's data of exchange n before it can produce n+1).
+struct P2PPush {
+  int64_t nsnd;
+  const int *snd_ids;                     // own local ids to send, grouped by neighbour
+  const int *snd_nbr;                     // neighbour index of every element
+  const int64_t *snd_ptrs;                // n_nbr+1 group offsets
+  double *const *peer_buf;                // per neighbour: my slot in its receive buffer (this parity)
+  unsigned long long *const *peer_flag;   // per neighbour: its flag word for me
+  int n_nbr;
+  unsigned long long seq;
+  unsigned int *ticket;
+};
+__global__ void __launch_bounds__(256) p2p_push_kernel(P2PPush p, const double *__restrict__ v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.nsnd; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = p.snd_nbr[i];
+    p.peer_buf[k][i - p.snd_ptrs[k]] = v[p.snd_ids[i]];
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool is_last;
+  if (threadIdx.x == 0) is_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (is_last) {
+    __threadfence_system();
+    for (int k = threadIdx.x; k < p.n_nbr; k += blockDim.x) {
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.peer_flag[k]), "l"(p.seq) : "memory");
+    }
+    if (threadIdx.x == 0) *p.ticket = 0u;
+  }
+}
+
+struct P2PWait {
+  int n_nbr;
+  const int *nbr_rank;                    // ranks I receive from
+  const unsigned long long *flags;        // my flag words, indexed by sender rank
+  unsigned long long seq;
+  int64_t nrcv;
+  const int *rcv_ids;                     // ghost local ids, grouped by neighbour
+  const double *rcv_buf;                  // this parity
+};
+__global__ void __launch_bounds__(256) p2p_wait_unpack_kernel(P2PWait w, double *__restrict__ v) {
+  if (threadIdx.x < w.n_nbr) {
+    const unsigned long long *f = w.flags + w.nbr_rank[threadIdx.x];
+    const long long t0 = clock64();
+    for (;;) {
+      unsigned long long cur;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(cur) : "l"(f) : "memory");
+      if (cur >= w.seq) break;
+      if (clock64() - t0 > 20000000000LL) __trap();  // ~10 s: a peer died; fail instead of hanging
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < w.nrcv; i += (int64_t)gridDim.x * blockDim.x)
+    v[w.rcv_ids[i]] = __ldcg(w.rcv_buf + i);
 }
 
 // diag extraction: invd[i] = 1/A[i,i]  (JacobiLinearSolvers.jl:20-23,29-34; own-own block)

@@ -29,6 +29,11 @@ void spmv(gsb_mat_t A, gsb_vec_s &x, gsb_vec_s &y, double alpha, double beta);  
 void resid(gsb_mat_t A, gsb_vec_s &x, const gsb_vec_s &b, gsb_vec_s &out);             // out = b - A x
 void sweep(gsb_mat_t A, gsb_vec_s &dx_in, gsb_vec_s &r, const double *invd, double omega, gsb_vec_s &dx_out,
            gsb_vec_s &xacc);                                                            // fused Jacobi-Richardson sweep
+// niter fused sweeps r -= A dx ; dx' = omega*(invd.*r) ; x += dx' (the last one only updates r), S at a
+// time in one launch through the L2-pipelined kernel; dx_0 must be in dxa.  Returns false (and does
+// nothing) when the matrix is not eligible -- the caller then issues one launch per sweep.
+bool sweeps_pipelined(gsb_mat_t A, const double *invd, double omega, int niter, gsb_vec_s &r, gsb_vec_s &x,
+                      gsb_vec_s &dxa, gsb_vec_s &dxb);
 void spmv_dot(gsb_mat_t A, gsb_vec_s &x, gsb_vec_s &y, const gsb_vec_s &dotv, int slot); // y = A x ; scal[slot] = dotv.y
 void spmv_add(gsb_mat_t A, gsb_vec_s &x, gsb_vec_s &y, gsb_vec_s &xacc);                // y = A x ; xacc += y
 

@@ -100,6 +100,8 @@ struct RichardsonNS : gsb_solver_s {
       if (niter <= 0) return;
       // iteration 1 prologue: dx = w*(invD*r) ; x += dx          (:91-93)
       jacobi_step(J->invd.p, r, omega, *dx, x, x_is_zero);
+      // large single-part levels: S sweeps per launch, matrix re-read from L2 (bit-identical result)
+      if (sweeps_pipelined(A, J->invd.p, omega, niter, r, x, *dx, *Adx)) return;
       for (int it = 1; it <= niter; ++it) {
         if (it < niter) {
           // r -= A dx  (:94-95) fused with the next iteration's dx = w*(invD*r) ; x += dx

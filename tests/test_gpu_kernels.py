@@ -192,6 +192,41 @@ def test_richardson_jacobi_bit_exact(gsb, ctx, nc, kernel):
         ctx.set_option("fuse_smoother", "1")
 
 
+@pytest.mark.parametrize("nc,force", [((20, 24, 16), True), ((33, 17), True), ((96, 96, 80), False)])
+@pytest.mark.parametrize("stages", [2, 3, 5, 10])
+def test_richardson_l2_pipelined_sweeps_bit_exact(gsb, ctx, nc, force, stages):
+    """S sweeps fused in one launch (inter-CTA dependency pipeline through L2) == the reference sequence, bit for bit"""
+    from gsb200 import synth
+    from util import host_to_scipy
+
+    ctx.set_option("pipe_stages", stages)
+    ctx.set_option("pipe_min_chunks", 1 if force else 2368)
+    try:
+        hh = synth.poisson_hierarchy_host(nc, 1)
+        n = hh.levels[0].n_own
+        As = host_to_scipy(hh.A[0], n)
+        A, Ao = dev_matrix(gsb, ctx, As), ola.CSR(As)
+        for niter in (10, 3):
+            s = gsb.RichardsonSmoother(gsb.JacobiLinearSolver(), niter, 2.0 / 3.0)
+            ns = gsb.numerical_setup(gsb.symbolic_setup(s, A), A)
+            x0, r0 = _rand(n, 31), _rand(n, 32)
+            xd, rd = dev_vec(gsb, A, x0), dev_vec(gsb, A, r0)
+            l0 = ctx.launch_count()
+            gsb.solve_(xd, ns, rd)
+            assert ctx.launch_count() - l0 == 1 + -(-niter // stages)  # prologue + ceil(niter/S) launches
+            so = OS.RichardsonSmoother(OS.JacobiLinearSolver(), niter, 2.0 / 3.0)
+            xo, ro = x0.copy(), r0.copy()
+            OS.solve_(xo, OS.numerical_setup(OS.symbolic_setup(so, Ao), Ao), ro)
+            assert np.array_equal(xd.get(), xo) and np.array_equal(rd.get(), ro)
+            # run to run reproducible
+            xd2, rd2 = dev_vec(gsb, A, x0), dev_vec(gsb, A, r0)
+            gsb.solve_(xd2, ns, rd2)
+            assert np.array_equal(xd2.get(), xo) and np.array_equal(rd2.get(), ro)
+    finally:
+        ctx.set_option("pipe_stages", 1)
+        ctx.set_option("pipe_min_chunks", 2368)
+
+
 def test_linear_solver_from_smoother(gsb, ctx):
     sysm = fem.poisson((10, 10))
     A, Ao = dev_matrix(gsb, ctx, sysm.A), ola.CSR(sysm.A)
