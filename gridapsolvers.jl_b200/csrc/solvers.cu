@@ -258,9 +258,37 @@ struct GMGNS : gsb_solver_s {
     ctx->hint_vec = nullptr;
     if (log.maxiter == 1 && have_hint && !(1.0 < log.rtol) && ctx->hint_norm > 4.0 * log.atol &&
         std::isfinite(ctx->hint_norm) && ctx->opt("gmg_defer_log", "1") == "1") {
-      dot(*rh, *rh, slot_rr);
-      cycle(cycle_type, 0, x, *rh);
-      dot(*rh, *rh, slot_rr + 1);
+      // single rank: the whole application (norm, V-cycle, norm: ~100 launches, most of them tiny
+      // coarse-level kernels) is captured once into a CUDA graph and replayed
+      const bool use_graph = ctx->nranks == 1 && !ctx->profiling && ctx->opt("graph", "1") == "1";
+      if (use_graph && graph_exec && graph_x == x.d && graph_b == b.d) {
+        GSB_CUDA(cudaGraphLaunch(graph_exec, ctx->stream));
+        ctx->launches += graph_launches;
+      } else if (use_graph) {
+        if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+        const int64_t l0 = ctx->launches;
+        cudaGraph_t g = nullptr;
+        GSB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        try {
+          dot(*rh, *rh, slot_rr);
+          cycle(cycle_type, 0, x, *rh);
+          dot(*rh, *rh, slot_rr + 1);
+        } catch (...) {
+          cudaStreamEndCapture(ctx->stream, &g);
+          if (g) cudaGraphDestroy(g);
+          throw;
+        }
+        GSB_CUDA(cudaStreamEndCapture(ctx->stream, &g));
+        graph_launches = ctx->launches - l0;
+        GSB_CUDA(cudaGraphInstantiate(&graph_exec, g, 0));
+        GSB_CUDA(cudaGraphDestroy(g));
+        graph_x = x.d; graph_b = b.d;
+        GSB_CUDA(cudaGraphLaunch(graph_exec, ctx->stream));
+      } else {
+        dot(*rh, *rh, slot_rr);
+        cycle(cycle_type, 0, x, *rh);
+        dot(*rh, *rh, slot_rr + 1);
+      }
       pending = true;
       return;
     }
@@ -274,6 +302,12 @@ struct GMGNS : gsb_solver_s {
     log.finalize(res);
   }
   bool pending = false;
+  cudaGraphExec_t graph_exec = nullptr;
+  const double *graph_x = nullptr, *graph_b = nullptr;
+  int64_t graph_launches = 0;
+  ~GMGNS() override {
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
+  }
   void finish() override {
     if (!pending) return;
     double v[2];
