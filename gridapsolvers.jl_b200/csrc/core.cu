@@ -185,16 +185,15 @@ static void exchange_on(gsb_vec_s &v, gsb_plan_t plan, cudaStream_t st) {
   gsb_ctx_t ctx = v.ctx;
   const int64_t nsnd = plan->snd_ptrs.back(), nrcv = plan->rcv_ptrs.back();
   if (plan->p2p) {
-    plan->seq += 1;
-    const int par = (int)(plan->seq & 1ull);
-    P2PPush ps{nsnd, plan->snd_ids.p, plan->snd_nbr.p, plan->snd_ptrs_dev.p, plan->peer_buf[par].p, plan->peer_flag.p,
-               (int)plan->nbr_snd.size(), plan->seq, plan->ticket.p};
+    P2PPush ps{nsnd, plan->snd_ids.p, plan->snd_nbr.p, plan->snd_ptrs_dev.p, plan->peer_buf[0].p, plan->peer_buf[1].p,
+               plan->peer_flag.p, (int)plan->nbr_snd.size(), plan->seq_dev.p, plan->ticket.p};
     const int g1 = (int)std::max<int64_t>(1, std::min<int64_t>((nsnd + 255) / 256, 2 * ctx->num_sms));
     p2p_push_kernel<<<g1, 256, 0, st>>>(ps, v.d);
     launched(ctx);
-    const double *rb = (const double *)((char *)plan->block + plan->flag_bytes) + (size_t)par * (size_t)std::max<int64_t>(nrcv, 1);
-    P2PWait pw{(int)plan->nbr_rcv.size(), plan->nbr_rcv_dev.p, (const unsigned long long *)plan->block, plan->seq, nrcv,
-               plan->rcv_ids.p, rb};
+    const double *rb0 = (const double *)((char *)plan->block + plan->flag_bytes);
+    const double *rb1 = rb0 + (size_t)std::max<int64_t>(nrcv, 1);
+    P2PWait pw{(int)plan->nbr_rcv.size(), plan->nbr_rcv_dev.p, (const unsigned long long *)plan->block, plan->seq_dev.p, nrcv,
+               plan->rcv_ids.p, rb0, rb1};
     const int g2 = (int)std::max<int64_t>(1, std::min<int64_t>((nrcv + 255) / 256, 2 * ctx->num_sms));
     p2p_wait_unpack_kernel<<<g2, 256, 0, st>>>(pw, v.d);
     launched(ctx);
@@ -330,7 +329,7 @@ static void launch_sell_split(gsb_mat_t A, RowArgs &a, gsb_vec_s &xvec) {
 static bool use_split(gsb_mat_t A) {
   gsb_ctx_t ctx = A->ctx;
   const bool force = ctx->opt("force_split", "0") == "1";  // diagnostics: split kernels on one rank
-  return A->split_ok && A->sell_ok && ((ctx->nranks > 1 && A->plan) || force) && ctx->opt("overlap", "1") == "1" &&
+  return A->split_ok && A->sell_ok && ((ctx->nranks > 1 && A->plan) || force) && ctx->opt("overlap", "0") == "1" &&
          ctx->opt("spmv", "auto") != "vector" && ctx->opt("spmv", "auto") != "stream" &&
          A->n_rows >= (int64_t)std::stoll(ctx->opt("overlap_min_rows", "100000"));
 }
@@ -920,6 +919,8 @@ static void setup_p2p(gsb_plan_s *p) {
     GSB_CUDA(cudaMemcpy(p->nbr_rcv_dev.p, p->nbr_rcv.data(), sizeof(int) * p->nbr_rcv.size(), cudaMemcpyHostToDevice));
   p->ticket.alloc(1);
   GSB_CUDA(cudaMemset(p->ticket.p, 0, sizeof(unsigned int)));
+  p->seq_dev.alloc(1);
+  GSB_CUDA(cudaMemset(p->seq_dev.p, 0, sizeof(unsigned long long)));
   // nobody may push before every rank has zeroed its flags and mapped its peers
   DevBuf<double> tok(1);
   GSB_CUDA(cudaMemset(tok.p, 0, sizeof(double)));

@@ -111,7 +111,7 @@ struct gsb_plan_s {
   bool rcv_contiguous = false;  // ghosts of each neighbour form one ascending run -> no unpack
   // NVLink peer-memory exchange (CUDA IPC); see kernels.cuh p2p_push_kernel
   bool p2p = false;
-  unsigned long long seq = 0;
+  gsb::DevBuf<unsigned long long> seq_dev;  // exchange counter lives on the device (graph replay)
   void *block = nullptr;                 // [flags: nranks u64 | buf parity 0 | buf parity 1]
   size_t flag_bytes = 0;
   std::vector<void *> peer_base;         // opened IPC mappings of the send neighbours' blocks

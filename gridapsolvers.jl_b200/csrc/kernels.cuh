@@ -839,16 +839,19 @@ struct P2PPush {
   const int *snd_ids;                     // own local ids to send, grouped by neighbour
   const int *snd_nbr;                     // neighbour index of every element
   const int64_t *snd_ptrs;                // n_nbr+1 group offsets
-  double *const *peer_buf;                // per neighbour: my slot in its receive buffer (this parity)
+  double *const *peer_buf0;               // per neighbour: my slot in its receive buffer, parity 0 / 1
+  double *const *peer_buf1;
   unsigned long long *const *peer_flag;   // per neighbour: its flag word for me
   int n_nbr;
-  unsigned long long seq;
+  unsigned long long *seq;                // device-resident exchange counter (CUDA-graph replayable)
   unsigned int *ticket;
 };
 __global__ void __launch_bounds__(256) p2p_push_kernel(P2PPush p, const double *__restrict__ v) {
+  const unsigned long long seq = *(volatile unsigned long long *)p.seq + 1ull;  // this exchange's number
+  double *const *peer_buf = (seq & 1ull) ? p.peer_buf1 : p.peer_buf0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.nsnd; i += (int64_t)gridDim.x * blockDim.x) {
     const int k = p.snd_nbr[i];
-    p.peer_buf[k][i - p.snd_ptrs[k]] = v[p.snd_ids[i]];
+    peer_buf[k][i - p.snd_ptrs[k]] = v[p.snd_ids[i]];
   }
   __threadfence_system();
   __syncthreads();
@@ -858,9 +861,12 @@ __global__ void __launch_bounds__(256) p2p_push_kernel(P2PPush p, const double *
   if (is_last) {
     __threadfence_system();
     for (int k = threadIdx.x; k < p.n_nbr; k += blockDim.x) {
-      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.peer_flag[k]), "l"(p.seq) : "memory");
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.peer_flag[k]), "l"(seq) : "memory");
     }
-    if (threadIdx.x == 0) *p.ticket = 0u;
+    if (threadIdx.x == 0) {
+      *p.ticket = 0u;
+      *p.seq = seq;  // every block has read the old value before arriving at the ticket
+    }
   }
 }
 
@@ -868,26 +874,29 @@ struct P2PWait {
   int n_nbr;
   const int *nbr_rank;                    // ranks I receive from
   const unsigned long long *flags;        // my flag words, indexed by sender rank
-  unsigned long long seq;
+  const unsigned long long *seq;          // device counter, already advanced by the push kernel
   int64_t nrcv;
   const int *rcv_ids;                     // ghost local ids, grouped by neighbour
-  const double *rcv_buf;                  // this parity
+  const double *rcv_buf0;                 // parity 0 / 1
+  const double *rcv_buf1;
 };
 __global__ void __launch_bounds__(256) p2p_wait_unpack_kernel(P2PWait w, double *__restrict__ v) {
+  const unsigned long long seq = *w.seq;
+  const double *rcv_buf = (seq & 1ull) ? w.rcv_buf1 : w.rcv_buf0;
   if (threadIdx.x < w.n_nbr) {
     const unsigned long long *f = w.flags + w.nbr_rank[threadIdx.x];
     const long long t0 = clock64();
     for (;;) {
       unsigned long long cur;
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(cur) : "l"(f) : "memory");
-      if (cur >= w.seq) break;
+      if (cur >= seq) break;
       if (clock64() - t0 > 20000000000LL) __trap();  // ~10 s: a peer died; fail instead of hanging
       __nanosleep(64);
     }
   }
   __syncthreads();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < w.nrcv; i += (int64_t)gridDim.x * blockDim.x)
-    v[w.rcv_ids[i]] = __ldcg(w.rcv_buf + i);
+    v[w.rcv_ids[i]] = __ldcg(rcv_buf + i);
 }
 
 // diag extraction: invd[i] = 1/A[i,i]  (JacobiLinearSolvers.jl:20-23,29-34; own-own block)

@@ -260,7 +260,10 @@ struct GMGNS : gsb_solver_s {
         std::isfinite(ctx->hint_norm) && ctx->opt("gmg_defer_log", "1") == "1") {
       // single rank: the whole application (norm, V-cycle, norm: ~100 launches, most of them tiny
       // coarse-level kernels) is captured once into a CUDA graph and replayed
-      const bool use_graph = ctx->nranks == 1 && !ctx->profiling && ctx->opt("graph", "1") == "1";
+      // (multi-rank: NCCL collectives are capturable and the peer-memory halo exchange keeps its
+      //  sequence number on the device, so the replay is valid there too; the two-stream overlap is not)
+      const bool use_graph = !ctx->profiling && ctx->opt("graph", "1") == "1" &&
+                             (ctx->nranks == 1 || (ctx->opt("p2p", "1") == "1" && ctx->opt("overlap", "0") != "1"));
       if (use_graph && graph_exec && graph_x == x.d && graph_b == b.d) {
         GSB_CUDA(cudaGraphLaunch(graph_exec, ctx->stream));
         ctx->launches += graph_launches;

@@ -54,6 +54,7 @@ def main():
     assert np.array_equal(x.get_local(), xg[gid]), "ghost values differ from owners'"
 
     # 2. SpMV (the "auto" runs use the own/ghost split with the halo exchange overlapped on a second stream)
+    ctx.set_option("overlap", "1")
     ctx.set_option("overlap_min_rows", os.environ.get("MGPU_OVERLAP_MIN_ROWS", "1"))
     for kern in ("auto", "sell", "stream", "vector"):
         ctx.set_option("spmv", kern)
@@ -74,7 +75,8 @@ def main():
     d = gsb.dot(x, x)
     assert abs(d - float(xg @ xg)) <= 1e-13 * float(xg @ xg)
 
-    # 3. GMG-PCG vs the serial oracle
+    # 3. GMG-PCG vs the serial oracle: (a) overlapped two-stream halo exchange, (b) default path
+    #    (peer-memory exchange inside a replayed CUDA graph); both must give the same history
     sm = gsb.Fill(gsb.RichardsonSmoother(gsb.JacobiLinearSolver(), 10, 2.0 / 3.0), nlev - 1)
     gmg = gsb.GMGLinearSolver(dh.A, dh.P, dh.R, pre_smoothers=sm, post_smoothers=sm, maxiter=1)
     s = gsb.CGSolver(gmg, maxiter=30, atol=1e-14, rtol=1e-8)
@@ -82,6 +84,12 @@ def main():
     xs, b = gsb.allocate_in_domain(A), gsb.allocate_in_domain(A)
     b.set(hh.b)
     gsb.solve_(xs, ns, b)
+    hist_overlap = s.log.history()
+    ctx.set_option("overlap", "0")
+    for _ in range(2):  # second solve replays the captured graph
+        xs.fill(0.0)
+        gsb.solve_(xs, ns, b)
+        assert np.array_equal(s.log.history(), hist_overlap), "graph / overlap paths disagree"
     err = float(np.max(np.abs(xs.get() - synth.exact_solution(lp))))
     if rank == 0:
         hs = synth.poisson_hierarchy_host(ncell, nlev, lengths=lengths)
