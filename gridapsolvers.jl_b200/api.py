@@ -126,6 +126,13 @@ class ExchangePlan:
                                          len(k[3]), _ptr(k[3]), _ptr(k[4]), _ptr(k[5]), index_base, ctypes.byref(h)))
         self.h, self.n_own, self.n_ghost = h, n_own, n_ghost
 
+    def __del__(self):
+        try:
+            if self.h:
+                _lib.lib().gsb_plan_destroy(self.h)
+        except Exception:
+            pass
+
 
 class SparseMatrix:
     """Device mirror of the local block of a PSparseMatrix (own rows x own+ghost columns)."""

@@ -86,12 +86,8 @@ void vec_fill(gsb_vec_s &v, double val) {
   if (val == 0.0) {
     GSB_CUDA(cudaMemsetAsync(v.d, 0, sizeof(double) * v.n_local(), v.ctx->stream));
   } else {
-    EwArgs g{};
-    // z = a*x with x := z is not a fill; use a tiny dedicated path: a*1 via has_d trick is overkill
-    std::vector<double> h((size_t)v.n_local(), val);
-    GSB_CUDA(cudaMemcpyAsync(v.d, h.data(), sizeof(double) * v.n_local(), cudaMemcpyHostToDevice, v.ctx->stream));
-    GSB_CUDA(cudaStreamSynchronize(v.ctx->stream));
-    (void)g;
+    fill_kernel<<<ew_grid(v.ctx, v.n_local()), EW_THREADS, 0, v.ctx->stream>>>(v.n_local(), val, v.d);
+    launched(v.ctx);
   }
 }
 

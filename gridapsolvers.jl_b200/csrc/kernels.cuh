@@ -756,6 +756,10 @@ __global__ void __launch_bounds__(THREADS) ew_kernel(EwArgs g) {
   }
 }
 
+__global__ void fill_kernel(int64_t n, double value, double *__restrict__ v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[i] = value;
+}
+
 // Jacobi-Richardson prologue: dx = omega*(invd*r) ; x += dx      (RichardsonSmoothers.jl:91-93)
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) jacobi_step_kernel(int64_t n, const double *__restrict__ invd,

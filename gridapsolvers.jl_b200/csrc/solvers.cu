@@ -267,7 +267,9 @@ struct GMGNS : gsb_solver_s {
       if (use_graph && graph_exec && graph_x == x.d && graph_b == b.d) {
         GSB_CUDA(cudaGraphLaunch(graph_exec, ctx->stream));
         ctx->launches += graph_launches;
-      } else if (use_graph) {
+      } else if (use_graph && last_x == x.d && last_b == b.d) {
+        // second consecutive application on the same vector pair (the PCG pattern): worth capturing.
+        // Callers that pass a different pair every time (FGMRES: Z[j], V[j]) never pay for a capture.
         if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
         const int64_t l0 = ctx->launches;
         cudaGraph_t g = nullptr;
@@ -292,6 +294,7 @@ struct GMGNS : gsb_solver_s {
         cycle(cycle_type, 0, x, *rh);
         dot(*rh, *rh, slot_rr + 1);
       }
+      last_x = x.d; last_b = b.d;
       pending = true;
       return;
     }
@@ -306,7 +309,7 @@ struct GMGNS : gsb_solver_s {
   }
   bool pending = false;
   cudaGraphExec_t graph_exec = nullptr;
-  const double *graph_x = nullptr, *graph_b = nullptr;
+  const double *graph_x = nullptr, *graph_b = nullptr, *last_x = nullptr, *last_b = nullptr;
   int64_t graph_launches = 0;
   ~GMGNS() override {
     if (graph_exec) cudaGraphExecDestroy(graph_exec);

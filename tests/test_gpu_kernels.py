@@ -158,6 +158,10 @@ def test_blas1(gsb, ctx):
     assert np.array_equal(zd.get(), 2.0 * a + b)
     # reductions are deterministic run to run
     assert gsb.dot(ad, bd) == gsb.dot(ad, bd)
+    zd.fill(2.5)
+    assert np.array_equal(zd.get(), np.full(n, 2.5))
+    zd.fill(0.0)
+    assert not zd.get().any()
 
 
 @pytest.mark.parametrize("nc", [(16, 16), (12, 12, 12)])
