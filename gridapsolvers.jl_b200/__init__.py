@@ -10,4 +10,5 @@ from .api import (Context, ExchangePlan, SparseMatrix, BlockSparseMatrix, Vector
                   mul_, dot, norm, axpby_, copy_, consistent_, SolverTolerances, ConvergenceLog, symbolic_setup,
                   numerical_setup, numerical_setup_, solve_, ldiv_, IdentitySolver, JacobiLinearSolver, LUSolver,
                   RichardsonSmoother, LinearSolverFromSmoother, Fill, GMGLinearSolver, CGSolver, GMRESSolver,
-                  FGMRESSolver, MINRESSolver, BlockTriangularSolver, BlockDiagonalSolver)
+                  FGMRESSolver, MINRESSolver, BlockTriangularSolver, BlockDiagonalSolver, LanczosDiagnostic,
+                  RichardsonLinearSolver, SchurComplementSolver)

@@ -68,6 +68,10 @@ SIGNATURES = {
     "gsb_fgmres_create": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_d, c_d, PP(c_p)],
     "gsb_minres_create": [c_p, c_p, c_i, c_d, c_d, PP(c_p)],
     "gsb_block_solver_create": [c_p, c_i, PP(c_p), PP(c_p), c_p, c_i, c_i, PP(c_p)],
+    "gsb_richardson_linear_create": [c_p, c_p, c_d, c_i, c_d, c_d, PP(c_p)],
+    "gsb_schur_complement_create": [c_p, c_p, c_p, c_p, c_p, PP(c_p)],
+    "gsb_cg_record_coefficients": [c_p, c_i],
+    "gsb_cg_coefficients": [c_p, c_p, c_p, c_i64, PP(c_i64)],
     "gsb_solver_update": [c_p, c_p],
     "gsb_solve": [c_p, c_p, c_p],
     "gsb_solve_host": [c_p, c_p, c_p, c_i64],

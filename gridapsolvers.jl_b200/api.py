@@ -376,6 +376,8 @@ def solve_(x, ns: NumericalSetup, b):
     else:
         check(L.gsb_solve(ns.h, x.h, b.h))
     ns._logs()
+    if getattr(ns, "_after_solve", None) is not None:
+        ns._after_solve(ns)
     return x
 
 
@@ -483,9 +485,44 @@ class GMGLinearSolver(LinearSolver):
         return NumericalSetup(self, h, kids, mat=mat)
 
 
+class LanczosDiagnostic:
+    """Krylov/KrylovUtils.jl:58-90: (delta, gamma) of the Lanczos tridiagonal recorded from CG's alpha/beta
+    (CGSolvers.jl:122-138); `estimate()` = condition-number estimate |lambda_max / lambda_min|."""
+
+    def __init__(self, max_iters: int):
+        self.k = 0
+        self.delta = np.zeros(max_iters)
+        self.gamma = np.zeros(max_iters)
+
+    def reset(self):
+        self.k = 0
+        self.delta[:] = 0
+        self.gamma[:] = 0
+
+    def _update_from(self, alpha, beta):
+        self.reset()
+        a_last = 1.0
+        for a, b in zip(alpha, beta):
+            if self.k == 0:
+                d, g = 1.0 / a, 0.0
+            else:
+                d, g = (1.0 / a) + (b / a_last), math.sqrt(b) / a
+            self.delta[self.k], self.gamma[self.k] = d, g
+            self.k += 1
+            a_last = a
+
+    def estimate(self) -> float:
+        k = self.k
+        if k < 2:
+            return 1.0
+        T = np.diag(self.delta[:k]) + np.diag(self.gamma[1:k], 1) + np.diag(self.gamma[1:k], -1)
+        lam = np.linalg.eigvalsh(T)
+        return float(abs(lam.max() / lam.min()))
+
+
 class CGSolver(LinearSolver):
-    def __init__(self, Pl=None, maxiter=1000, atol=1e-12, rtol=1.0e-6, flexible=False, verbose=0, name="CG"):
-        self.Pl, self.flexible = Pl, bool(flexible)
+    def __init__(self, Pl=None, maxiter=1000, atol=1e-12, rtol=1.0e-6, diagnostic=None, flexible=False, verbose=0, name="CG"):
+        self.Pl, self.flexible, self.diag = Pl, bool(flexible), diagnostic
         self.log = ConvergenceLog(name, SolverTolerances(maxiter=maxiter, atol=atol, rtol=rtol), verbose=verbose)
 
     def _numerical_setup(self, A):
@@ -493,7 +530,44 @@ class CGSolver(LinearSolver):
         t = self.log.tols
         h = c_p()
         check(_lib.lib().gsb_cg_create(A.h, _h(Pl), int(self.flexible), t.maxiter, t.atol, t.rtol, ctypes.byref(h)))
+        ns = NumericalSetup(self, h, [Pl], mat=A)
+        if self.diag is not None:
+            check(_lib.lib().gsb_cg_record_coefficients(h, 1))
+            ns._after_solve = self._fill_diagnostic
+        return ns
+
+    def _fill_diagnostic(self, ns):
+        cap = self.log.tols.maxiter
+        alpha, beta, n = np.zeros(cap), np.zeros(cap), ctypes.c_int64()
+        check(_lib.lib().gsb_cg_coefficients(ns.h, _ptr(alpha), _ptr(beta), cap, ctypes.byref(n)))
+        self.diag._update_from(alpha[: n.value], beta[: n.value])
+
+
+class RichardsonLinearSolver(LinearSolver):
+    """RichardsonLinearSolver(omega, maxiter; Pl, rtol, atol) -- RichardsonLinearSolvers.jl:12-23 (scalar omega)"""
+
+    def __init__(self, omega, maxiter, Pl=None, rtol=1e-10, atol=1e-6, verbose=False, name="RichardsonLinearSolver"):
+        self.omega, self.Pl = float(omega), Pl
+        self.log = ConvergenceLog(name, SolverTolerances(maxiter=maxiter, atol=atol, rtol=rtol), verbose=verbose)
+
+    def _numerical_setup(self, A):
+        Pl = _child(self.Pl, A)
+        t = self.log.tols
+        h = c_p()
+        check(_lib.lib().gsb_richardson_linear_create(A.h, _h(Pl), self.omega, t.maxiter, t.atol, t.rtol, ctypes.byref(h)))
         return NumericalSetup(self, h, [Pl], mat=A)
+
+
+class SchurComplementSolver(LinearSolver):
+    """SchurComplementSolver(A_ns, B, C, S_ns) -- SchurComplementSolvers.jl:8-24; A_ns, S_ns are NumericalSetups"""
+
+    def __init__(self, A_ns, B, C, S_ns):
+        self.A, self.B, self.C, self.S = A_ns, B, C, S_ns
+
+    def _numerical_setup(self, mat):
+        h = c_p()
+        check(_lib.lib().gsb_schur_complement_create(self.B.ctx.h, self.A.h, self.B.h, self.C.h, self.S.h, ctypes.byref(h)))
+        return NumericalSetup(self, h, [self.A, self.S], mat=mat)
 
 
 class GMRESSolver(LinearSolver):

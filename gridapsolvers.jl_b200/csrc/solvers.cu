@@ -332,7 +332,9 @@ struct CGNS : gsb_solver_s {
   gsb_solver_t Pl;
   bool flexible;
   VecP w, p, z, r;  // CGSolvers.jl:42-48
-  int s_g0, s_pw, s_rr, s_delta;
+  int s_g0, s_pw, s_rr, s_delta;  // five consecutive slots: gamma[2], p.w, r.r, delta
+  bool record = false;            // LanczosDiagnostic support: keep alpha_k, beta_k
+  std::vector<double> alphas, betas;
   const char *name() const override { return "CG"; }
   gsb_mat_t matrix() override { return A; }
   CGNS(gsb_mat_t A_, gsb_solver_t Pl_, bool flex, int maxiter, double atol, double rtol) : A(A_), Pl(Pl_), flexible(flex) {
@@ -351,6 +353,7 @@ struct CGNS : gsb_solver_s {
     vec_fill(*p, 0.0);                   // :80
     vec_fill(*z, 0.0);                   // :81
     int cur = 0;
+    alphas.clear(); betas.clear();
     set_slot(ctx, s_g0 + 1, 1.0);        // gamma = 1   :82
     dot(*r, *r, s_rr);
     double res = std::sqrt(ctx->read_scalar(s_rr));  // :85
@@ -379,7 +382,16 @@ struct CGNS : gsb_solver_s {
       ew_axpby(*p, imm(1.0), *zz, beta, p.get());                 // :101  p .= z .+ beta .* p
       spmv_dot(A, *p, *w, *p, s_pw);                              // :104-105
       cg_update(slot_ratio(gcur, s_pw), *p, *w, x, *r, s_rr);     // :105-109 alpha = gamma/dot(p,w)
-      res = std::sqrt(ctx->read_scalar(s_rr));                    // :111
+      if (record) {  // same IEEE operations the kernels perform on the device slots
+        double v[5];
+        ctx->read_scalars(s_g0, 5, v);
+        const double gc = v[cur], gp = v[1 - cur];
+        alphas.push_back(gc / v[2]);
+        betas.push_back((flexible && Pl) ? (gc - v[4]) / gp : gc / gp);
+        res = std::sqrt(v[3]);
+      } else {
+        res = std::sqrt(ctx->read_scalar(s_rr));                  // :111
+      }
       done = log.update(res);                                     // :112
       cur ^= 1;
     }
@@ -658,6 +670,75 @@ struct BlockNS : gsb_solver_s {
   }
 };
 
+// ---------------------------------------------------------------- RichardsonLinearSolver
+struct RichardsonLinearNS : gsb_solver_s {
+  gsb_mat_t A;
+  gsb_solver_t Pl;
+  double omega;
+  VecP z, r;  // RichardsonLinearSolvers.jl:33-40
+  int s_rr;
+  const char *name() const override { return "RichardsonLinearSolver"; }
+  gsb_mat_t matrix() override { return A; }
+  RichardsonLinearNS(gsb_mat_t A_, gsb_solver_t Pl_, double w, int maxiter, double atol, double rtol) : A(A_), Pl(Pl_), omega(w) {
+    ctx = A->ctx;
+    log.configure(maxiter, atol, rtol);
+    has_log = true;
+    z = domain_vec(A); r = domain_vec(A);
+    s_rr = ctx->alloc_slots(1);
+  }
+  void update(gsb_mat_t A_) override {
+    if (Pl) Pl->update(A_);
+    A = A_;
+  }
+  double residual(Vec &x, Vec &b) {  // r .= b ; mul!(r, A, x, -1, 1) ; norm(r)
+    vec_copy(*r, b);
+    spmv(A, x, *r, -1.0, 1.0);
+    dot(*r, *r, s_rr);
+    return std::sqrt(ctx->read_scalar(s_rr));
+  }
+  void solve(Vec &x, Vec &b) override {  // :79-106
+    double res = residual(x, b);
+    bool done = log.init(res);
+    while (!done) {
+      if (Pl) {
+        Pl->solve(*z, *r);
+        ew_axpby(x, imm(1.0), x, imm(omega), z.get());  // x .+= w .* z
+      } else {
+        ew_axpby(x, imm(1.0), x, imm(omega), r.get());
+      }
+      res = residual(x, b);
+      done = log.update(res);
+    }
+    log.finalize(res);
+  }
+};
+
+// ---------------------------------------------------------------- SchurComplementSolver
+struct SchurNS : gsb_solver_s {
+  gsb_solver_t A, S;
+  gsb_mat_t B, C;
+  VecP du, bu, bp;  // SchurComplementSolvers.jl:40-45
+  int64_t nu, np;
+  const char *name() const override { return "SchurComplement"; }
+  SchurNS(gsb_ctx_t c, gsb_solver_t A_, gsb_mat_t B_, gsb_mat_t C_, gsb_solver_t S_) : A(A_), S(S_), B(B_), C(C_) {
+    ctx = c;
+    GSB_CHECK(B->n_rows == C->n_own_cols && C->n_rows == B->n_own_cols, "Schur complement: B and C shapes do not match");
+    nu = B->n_rows; np = C->n_rows;
+    du = domain_vec(C); bu = domain_vec(C); bp = domain_vec(B);
+  }
+  void solve(Vec &x, Vec &y) override {  // :55-74
+    GSB_CHECK(x.n_own == nu + np && y.n_own == nu + np, "Schur complement: vector size mismatch");
+    Vec xu = view(x, 0, nu), xp = view(x, nu, np), yu = view(y, 0, nu), yp = view(y, nu, np);
+    A->solve(xu, yu);                                   // x_u = A^-1 y_u
+    vec_copy(*bp, yp);
+    spmv(C, xu, *bp, -1.0, 1.0);                        // bp = y_p - C x_u
+    S->solve(xp, *bp);                                  // x_p = S^-1 bp
+    spmv(B, xp, *bu, 1.0, 0.0);                         // bu = B x_p
+    A->solve(*du, *bu);                                 // du = A^-1 bu
+    ew_axpby(xu, imm(1.0), xu, imm(-1.0), du.get());    // x_u .-= du
+  }
+};
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------ C ABI
@@ -725,6 +806,35 @@ int gsb_block_solver_create(gsb_ctx_t ctx, int nb, const gsb_mat_t *blocks, cons
   API_BEGIN
   *out = new BlockNS(ctx, nb, blocks, solvers, coeffs, half, diagonal != 0);
   API_END(ctx)
+}
+
+int gsb_richardson_linear_create(gsb_mat_t A, gsb_solver_t Pl, double omega, int maxiter, double atol, double rtol,
+                                 gsb_solver_t *out) {
+  API_BEGIN
+  *out = new RichardsonLinearNS(A, Pl, omega, maxiter, atol, rtol);
+  API_END(A->ctx)
+}
+int gsb_schur_complement_create(gsb_ctx_t ctx, gsb_solver_t A_ns, gsb_mat_t B, gsb_mat_t C, gsb_solver_t S_ns,
+                                gsb_solver_t *out) {
+  API_BEGIN
+  GSB_CHECK(A_ns && S_ns && B && C, "Schur complement: NULL argument");
+  *out = new SchurNS(ctx, A_ns, B, C, S_ns);
+  API_END(ctx)
+}
+int gsb_cg_record_coefficients(gsb_solver_t ns, int enable) {
+  API_BEGIN
+  CGNS *cg = dynamic_cast<CGNS *>(ns);
+  GSB_CHECK(cg != nullptr, "not a CG numerical setup");
+  cg->record = enable != 0;
+  API_END(ns->ctx)
+}
+int gsb_cg_coefficients(gsb_solver_t ns, double *alpha, double *beta, int64_t cap, int64_t *n) {
+  API_BEGIN
+  CGNS *cg = dynamic_cast<CGNS *>(ns);
+  GSB_CHECK(cg != nullptr, "not a CG numerical setup");
+  *n = (int64_t)cg->alphas.size();
+  for (int64_t i = 0; i < std::min<int64_t>(cap, *n); ++i) { alpha[i] = cg->alphas[(size_t)i]; beta[i] = cg->betas[(size_t)i]; }
+  API_END(ns->ctx)
 }
 
 int gsb_solver_update(gsb_solver_t ns, gsb_mat_t A) {

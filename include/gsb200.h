@@ -166,6 +166,17 @@ int gsb_block_solver_create(gsb_ctx_t ctx, int nb, const gsb_mat_t *blocks, cons
 /* a block matrix acting on concatenated vectors, usable as the A of the Krylov solvers */
 int gsb_block_mat_create(gsb_ctx_t ctx, int nb, const gsb_mat_t *blocks, gsb_mat_t *out);
 
+/* RichardsonLinearSolver(omega,maxiter;Pl,rtol,atol), LinearSolvers/RichardsonLinearSolvers.jl:12-106 */
+int gsb_richardson_linear_create(gsb_mat_t A, gsb_solver_t Pl, double omega, int maxiter, double atol, double rtol,
+                                 gsb_solver_t *out);
+/* SchurComplementSolver(A_ns,B,C,S_ns) on a 2-block concatenated vector [u;p],
+ * LinearSolvers/SchurComplementSolvers.jl:8-74 */
+int gsb_schur_complement_create(gsb_ctx_t ctx, gsb_solver_t A_ns, gsb_mat_t B, gsb_mat_t C, gsb_solver_t S_ns,
+                                gsb_solver_t *out);
+/* LanczosDiagnostic support (Krylov/KrylovUtils.jl:58-90, CGSolvers.jl:122-138): record alpha_k, beta_k of a
+ * CG NumericalSetup during solve! and read them back (n = number recorded, at most cap copied) */
+int gsb_cg_record_coefficients(gsb_solver_t cg_ns, int enable);
+int gsb_cg_coefficients(gsb_solver_t cg_ns, double *alpha, double *beta, int64_t cap, int64_t *n);
 /* numerical_setup!(ns,A): refresh value-dependent data (inv_diag, dense inverse) after
  * gsb_mat_update_values; GMG-from-matrices does not support it (GMGLinearSolvers.jl:249-258). */
 int gsb_solver_update(gsb_solver_t ns, gsb_mat_t A);

@@ -17,6 +17,8 @@ Statement-by-statement CPU restatement of the reference's solve phase
   LinearSolvers/Krylov/MINRESSolvers.jl:75-149          -> MINRESSolver
   BlockSolvers/BlockTriangularSolvers.jl:188-242        -> BlockTriangularSolver
   BlockSolvers/BlockDiagonalSolvers.jl:165-177          -> BlockDiagonalSolver
+  LinearSolvers/RichardsonLinearSolvers.jl:79-106       -> RichardsonLinearSolver
+  LinearSolvers/SchurComplementSolvers.jl:55-74         -> SchurComplementSolver
   Gridap.Algebra.LUSolver (dep, UMFPACK)                -> LUSolver (SuperLU: exact sparse direct solve)
 
 Julia's `f!` is spelled `f_` here.  Vectors are numpy fp64 arrays; matrices are oracle.linalg.CSR.
@@ -842,4 +844,74 @@ class _BlockAdapterNS:
 
     def solve(self, x, b):
         self.ns.solve(self.A.split(x), self.A.split(b, self.A.rsizes))
+        return x
+
+
+# ------------------------------------------------------------------ "next" rows
+
+
+class RichardsonLinearSolver(_Solver):
+    """RichardsonLinearSolvers.jl:12-23 (scalar relaxation parameter)."""
+
+    def __init__(self, omega, maxiter, Pl=None, rtol=1e-10, atol=1e-6, verbose=0, name="RichardsonLinearSolver"):
+        self.omega, self.Pl = float(omega), Pl
+        self.log = ConvergenceLog(name, SolverTolerances(maxiter=maxiter, atol=atol, rtol=rtol), verbose=verbose)
+
+    def _numerical_setup(self, A):
+        return RichardsonLinearNS(self, A, _setup(self.Pl, A), allocate_in_domain(A), allocate_in_domain(A))
+
+
+class RichardsonLinearNS:
+    def __init__(self, solver, A, Pl_ns, z, r):
+        self.solver, self.A, self.Pl_ns, self.z, self.r = solver, A, Pl_ns, z, r
+
+    def update(self, A):
+        if self.Pl_ns is not None:
+            self.Pl_ns.update(A)
+        self.A = A
+        return self
+
+    def solve(self, x, b):  # :79-106
+        s, A, Pl, z, r, log = self.solver, self.A, self.Pl_ns, self.z, self.r, self.solver.log
+        r[:] = b
+        la.mul5(r, A, x, -1.0, 1.0)  # mul!(r, A, x, -1, 1)
+        done = init_(log, la.norm(r))
+        while not done:
+            if Pl is not None:
+                Pl.solve(z, r)
+                la.axpy(x, x, s.omega, z)  # x .+= w .* z
+            else:
+                la.axpy(x, x, s.omega, r)
+            r[:] = b
+            la.mul5(r, A, x, -1.0, 1.0)
+            done = update_(log, la.norm(r))
+        finalize_(log, la.norm(r))
+        return x
+
+
+class SchurComplementSolver(_Solver):
+    """SchurComplementSolvers.jl:8-24: A, S are NumericalSetups, B, C matrices; acts on [u; p]."""
+
+    def __init__(self, A_ns, B, C, S_ns):
+        self.A, self.B, self.C, self.S = A_ns, B, C, S_ns
+
+    def _numerical_setup(self, mat):
+        return SchurComplementNS(self, allocate_in_domain(self.C), allocate_in_domain(self.C), allocate_in_domain(self.B))
+
+
+class SchurComplementNS:
+    def __init__(self, solver, du, bu, bp):
+        self.s, self.du, self.bu, self.bp = solver, du, bu, bp
+
+    def solve(self, x, y):  # x, y: [u, p] lists of block vectors   :55-74
+        s = self.s
+        x_u, x_p = x
+        y_u, y_p = y
+        s.A.solve(x_u, y_u)
+        self.bp[:] = y_p
+        la.mul5(self.bp, s.C, x_u, -1.0, 1.0)
+        s.S.solve(x_p, self.bp)
+        la.mul(self.bu, s.B, x_p)
+        s.A.solve(self.du, self.bu)
+        la.sub(x_u, x_u, self.du)
         return x

@@ -188,3 +188,82 @@ def test_c2_full_size_properties(gsb, ctx):
     r2 = dev_vec(gsb, A, domain=False)
     gsb.mul_(r2, A, x2)
     assert np.array_equal(r2.get(), 2.0 * rd.get())
+
+
+def test_numerical_setup_update_refreshes_value_dependent_data(gsb, ctx):
+    """numerical_setup!(ns,A) after the matrix values changed (CGSolvers.jl:57-63, JacobiLinearSolvers.jl:25-41)"""
+    sysm = fem.poisson((8, 8, 8))
+    A = dev_matrix(gsb, ctx, sysm.A)
+    s = gsb.CGSolver(gsb.JacobiLinearSolver(), rtol=1e-10)
+    ns = gsb.numerical_setup(gsb.symbolic_setup(s, A), A)
+    xd = dev_vec(gsb, A)
+    gsb.solve_(xd, ns, dev_vec(gsb, A, sysm.b))
+    x1 = xd.get()
+    A.update_values(3.0 * sysm.A.data)  # same sparsity, new values
+    gsb.numerical_setup_(ns, A)
+    xd.fill(0.0)
+    gsb.solve_(xd, ns, dev_vec(gsb, A, sysm.b))
+    assert np.linalg.norm(3.0 * xd.get() - x1) <= 1e-8 * np.linalg.norm(x1)
+    so = OS.CGSolver(OS.JacobiLinearSolver(), rtol=1e-10)
+    Ao = ola.CSR(3.0 * sysm.A)
+    xo = np.zeros(Ao.shape[0])
+    OS.solve_(xo, OS.numerical_setup(OS.symbolic_setup(so, Ao), Ao), sysm.b)
+    assert s.log.num_iters == so.log.num_iters and rel_hist_diff(s.log.history(), so.log.history()) < HIST_TOL
+
+
+def test_richardson_linear_solver_parity(gsb, ctx):
+    sysm = fem.poisson((8, 8))
+    mk = lambda S: S.RichardsonLinearSolver(0.5, 1000, Pl=S.JacobiLinearSolver(), rtol=1e-8, atol=1e-14)
+    sg, so, xg, xo = _run_pair(gsb, ctx, sysm, mk, mk)
+    assert sg.log.num_iters == so.log.num_iters and sg.log.flag == so.log.flag
+    assert rel_hist_diff(sg.log.history(), so.log.history()) < HIST_TOL
+    assert fem.l2_error_sq(sysm, xg) < 1e-8
+    mk = lambda S: S.RichardsonLinearSolver(0.2, 25, rtol=1e-8, atol=1e-14)  # no preconditioner, stops at maxiter
+    sg, so, xg, xo = _run_pair(gsb, ctx, sysm, mk, mk)
+    assert sg.log.num_iters == so.log.num_iters == 25
+    assert rel_hist_diff(sg.log.history(), so.log.history()) < HIST_TOL
+
+
+def test_lanczos_diagnostic_matches_oracle(gsb, ctx):
+    """PCG-Jacobi with LanczosDiagnostic (KrylovTests.jl:96-137): condition-number estimate from CG's alpha/beta"""
+    sysm = fem.poisson((20, 20))
+    A, Ao = dev_matrix(gsb, ctx, sysm.A), ola.CSR(sysm.A)
+    dg, do = gsb.LanczosDiagnostic(400), OS.LanczosDiagnostic(400)
+    sg = gsb.CGSolver(gsb.JacobiLinearSolver(), maxiter=400, rtol=1e-12, diagnostic=dg)
+    so = OS.CGSolver(OS.JacobiLinearSolver(), maxiter=400, rtol=1e-12, diagnostic=do)
+    b = np.random.default_rng(0).standard_normal(Ao.shape[0])
+    ns = gsb.numerical_setup(gsb.symbolic_setup(sg, A), A)
+    gsb.solve_(dev_vec(gsb, A), ns, dev_vec(gsb, A, b))
+    xo = np.zeros(Ao.shape[0])
+    OS.solve_(xo, OS.numerical_setup(OS.symbolic_setup(so, Ao), Ao), b)
+    assert dg.k == sg.log.num_iters and abs(dg.k - do.k) <= 1
+    n = min(dg.k, do.k, 30)
+    assert np.allclose(dg.delta[:n], do.delta[:n], rtol=1e-9) and np.allclose(dg.gamma[:n], do.gamma[:n], rtol=1e-9)
+    Dm12 = 1.0 / np.sqrt(sysm.A.diagonal())
+    lam = np.linalg.eigvalsh((sysm.A.toarray() * Dm12).T * Dm12)
+    # (the reference's off-diagonal uses alpha_k rather than alpha_{k-1}, CGSolvers.jl:133, so its estimate is
+    #  only roughly the condition number of the preconditioned operator: 92 vs 80.9 here)
+    assert 0.5 * lam.max() / lam.min() < dg.estimate() < 1.5 * lam.max() / lam.min()
+    assert abs(dg.estimate() - do.estimate()) <= 1e-6 * do.estimate()
+
+
+def test_schur_complement_solver(gsb, ctx):
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+
+    st = fem.stokes_cavity((6, 6))
+    Au, B, Bt = st["A"], st["B"], st["Bt"]
+    D = -1e-2 * st["Mp"]
+    Sm = (D - B @ spla.spsolve(Au.tocsc(), Bt.tocsc())).tocsr()
+    Ag, Sg, Bg, Cg = (dev_matrix(gsb, ctx, m) for m in (Au, Sm, Bt, B))
+    A_ns = gsb.numerical_setup(gsb.symbolic_setup(gsb.LUSolver(), Ag), Ag)
+    S_ns = gsb.numerical_setup(gsb.symbolic_setup(gsb.LUSolver(), Sg), Sg)
+    sc = gsb.SchurComplementSolver(A_ns, Bg, Cg, S_ns)
+    ns = gsb.numerical_setup(gsb.symbolic_setup(sc, None), None)
+    n = Au.shape[0] + B.shape[0]
+    y = np.random.default_rng(2).standard_normal(n)
+    xd, yd = gsb.Vector(ctx, n), gsb.Vector(ctx, n)
+    yd.set(y)
+    gsb.solve_(xd, ns, yd)
+    M = sp.bmat([[Au, Bt], [B, D]], format="csr")
+    assert np.linalg.norm(M @ xd.get() - y) <= 1e-9 * np.linalg.norm(y)

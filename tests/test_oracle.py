@@ -151,3 +151,37 @@ def test_block_triangular_and_stokes_oracle():
     S.solve_(x, S.numerical_setup(S.symbolic_setup(s, M), M), b)
     assert np.linalg.norm(M.to_scipy() @ x - b) < 1e-7
     assert s.log.flag in (S.SOLVER_CONVERGED_RTOL, S.SOLVER_CONVERGED_ATOL)
+
+
+def test_richardson_linear_solver_known_answer():
+    """test/LinearSolvers/RichardsonLinearTests.jl: Richardson iteration with a Jacobi left preconditioner converges
+    to the discrete solution of the Poisson problem (L2 error^2 < 1e-8 there with rtol 1e-8)."""
+    sysm = fem.poisson((8, 8))
+    A = ola.CSR(sysm.A)
+    s = S.RichardsonLinearSolver(0.5, 1000, Pl=P(), rtol=1e-8, atol=1e-14)
+    x = S.allocate_in_domain(A)
+    S.solve_(x, S.numerical_setup(S.symbolic_setup(s, A), A), sysm.b)
+    assert s.log.flag == S.SOLVER_CONVERGED_RTOL
+    assert fem.l2_error_sq(sysm, x) < 1e-8
+    assert np.linalg.norm(sysm.A @ x - sysm.b) <= 1.01e-8 * np.linalg.norm(sysm.b)
+
+
+def test_schur_complement_solver_is_exact_block_inverse():
+    st = fem.stokes_cavity((6, 6))
+    Au, B, Bt = st["A"], st["B"], st["Bt"]
+    import scipy.sparse.linalg as spla
+    import scipy.sparse as sp
+
+    nu, npr = Au.shape[0], B.shape[0]
+    D = -1e-2 * st["Mp"]  # a stabilised (regular) 2x2 block system [[A, Bt], [B, D]]
+    Sm = (D - B @ spla.spsolve(Au.tocsc(), Bt.tocsc())).tocsr()
+    A_ns = S.numerical_setup(S.symbolic_setup(S.LUSolver(), ola.CSR(Au)), ola.CSR(Au))
+    S_ns = S.numerical_setup(S.symbolic_setup(S.LUSolver(), ola.CSR(Sm)), ola.CSR(Sm))
+    sc = S.SchurComplementSolver(A_ns, ola.CSR(Bt), ola.CSR(B), S_ns)
+    ns = sc._numerical_setup(None)
+    rng = np.random.default_rng(1)
+    y = [rng.standard_normal(nu), rng.standard_normal(npr)]
+    x = [np.zeros(nu), np.zeros(npr)]
+    ns.solve(x, y)
+    M = sp.bmat([[Au, Bt], [B, D]], format="csr")
+    assert np.linalg.norm(M @ np.concatenate(x) - np.concatenate(y)) <= 1e-9 * np.linalg.norm(np.concatenate(y))
