@@ -850,18 +850,32 @@ gsb_plan_s::~gsb_plan_s() {
 }
 
 // COLLECTIVE over all ranks (every rank creates its plans in the same order): exchanges the CUDA-IPC
-// handles of the receive blocks and the slot offsets, and maps the send neighbours' blocks.
+// handles of the receive blocks and the slot offsets, and maps the send neighbours' blocks.  If any rank
+// cannot export or map a block (no peer access between two GPUs, other node), every rank falls back to
+// the NCCL send/recv exchange for this plan -- the decision is taken collectively.
+static void release_p2p(gsb_plan_s *p) {
+  for (void *b : p->peer_base)
+    if (b) cudaIpcCloseMemHandle(b);
+  p->peer_base.clear();
+  if (p->block) cudaFree(p->block);
+  p->block = nullptr;
+  p->p2p = false;
+}
+
 static void setup_p2p(gsb_plan_s *p) {
   gsb_ctx_t ctx = p->ctx;
   const int R = ctx->nranks, me = ctx->rank;
   const int64_t nsnd = p->snd_ptrs.back(), nrcv = p->rcv_ptrs.back();
-  // all ranks must be able to map each other (same node, NVLink / PCIe P2P)
+  double ok = 1.0;
   p->flag_bytes = ((size_t)R * sizeof(unsigned long long) + 255) & ~(size_t)255;
   const size_t bytes = p->flag_bytes + 2 * sizeof(double) * (size_t)std::max<int64_t>(nrcv, 1);
-  GSB_CUDA(cudaMalloc(&p->block, bytes));
-  GSB_CUDA(cudaMemset(p->block, 0, bytes));
   cudaIpcMemHandle_t h;
-  GSB_CUDA(cudaIpcGetMemHandle(&h, p->block));
+  std::memset(&h, 0, sizeof(h));
+  if (cudaMalloc(&p->block, bytes) != cudaSuccess || cudaMemset(p->block, 0, bytes) != cudaSuccess ||
+      cudaIpcGetMemHandle(&h, p->block) != cudaSuccess) {
+    ok = 0.0;
+    (void)cudaGetLastError();
+  }
   // record per rank: [64 B handle | nrcv | off_from[0..R-1]]
   const size_t rec = 64 + sizeof(int64_t) * (size_t)(1 + R);
   std::vector<char> mine(rec, 0), all(rec * (size_t)R, 0);
@@ -879,7 +893,7 @@ static void setup_p2p(gsb_plan_s *p) {
   std::vector<double *> pb0(std::max<size_t>(nn, 1), nullptr), pb1(std::max<size_t>(nn, 1), nullptr);
   std::vector<unsigned long long *> pf(std::max<size_t>(nn, 1), nullptr);
   p->peer_base.assign(nn, nullptr);
-  for (size_t k = 0; k < nn; ++k) {
+  for (size_t k = 0; k < nn && ok > 0.0; ++k) {
     const int q = p->nbr_snd[k];
     const char *rq = all.data() + rec * (size_t)q;
     cudaIpcMemHandle_t hq;
@@ -888,7 +902,11 @@ static void setup_p2p(gsb_plan_s *p) {
     const int64_t nrcv_q = mq[0], off = mq[1 + me];
     GSB_CHECK(off >= 0, "p2p plan: neighbour " + std::to_string(q) + " does not expect data from rank " + std::to_string(me));
     void *base = nullptr;
-    GSB_CUDA(cudaIpcOpenMemHandle(&base, hq, cudaIpcMemLazyEnablePeerAccess));
+    if (cudaIpcOpenMemHandle(&base, hq, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      ok = 0.0;
+      (void)cudaGetLastError();
+      break;
+    }
     p->peer_base[k] = base;
     const size_t fb = ((size_t)R * sizeof(unsigned long long) + 255) & ~(size_t)255;
     double *buf0 = (double *)((char *)base + fb);
@@ -896,7 +914,18 @@ static void setup_p2p(gsb_plan_s *p) {
     pb1[k] = buf0 + (size_t)std::max<int64_t>(nrcv_q, 1) + off;
     pf[k] = (unsigned long long *)base + me;
   }
-  // parity 1 is used by the first exchange (seq = 1)
+  // collective verdict (also the barrier: nobody may push before every rank has zeroed its flags and
+  // mapped its peers): sum of the per-rank ok flags must be R
+  DevBuf<double> tok(1);
+  GSB_CUDA(cudaMemcpy(tok.p, &ok, sizeof(double), cudaMemcpyHostToDevice));
+  GSB_NCCL(ncclAllReduce(tok.p, tok.p, 1, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+  double total = 0.0;
+  GSB_CUDA(cudaMemcpyAsync(&total, tok.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  GSB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (total < (double)R - 0.5) {
+    release_p2p(p);
+    return;
+  }
   p->peer_buf[0].alloc(pb0.size());
   p->peer_buf[1].alloc(pb1.size());
   p->peer_flag.alloc(pf.size());
@@ -917,9 +946,7 @@ static void setup_p2p(gsb_plan_s *p) {
   GSB_CUDA(cudaMemset(p->ticket.p, 0, sizeof(unsigned int)));
   p->seq_dev.alloc(1);
   GSB_CUDA(cudaMemset(p->seq_dev.p, 0, sizeof(unsigned long long)));
-  // nobody may push before every rank has zeroed its flags and mapped its peers
-  DevBuf<double> tok(1);
-  GSB_CUDA(cudaMemset(tok.p, 0, sizeof(double)));
+  // second barrier: every rank's counters are initialised before anybody's first exchange
   GSB_NCCL(ncclAllReduce(tok.p, tok.p, 1, ncclDouble, ncclSum, ctx->comm, ctx->stream));
   GSB_CUDA(cudaStreamSynchronize(ctx->stream));
   p->p2p = true;
@@ -957,6 +984,7 @@ int gsb_plan_create(gsb_ctx_t ctx, int64_t n_own, int64_t n_ghost, int n_nbr_snd
   if (nsnd) GSB_CUDA(cudaMemcpy(p->snd_ids.p, s.data(), sizeof(int) * s.size(), cudaMemcpyHostToDevice));
   if (nrcv) GSB_CUDA(cudaMemcpy(p->rcv_ids.p, r.data(), sizeof(int) * r.size(), cudaMemcpyHostToDevice));
   if (ctx->nranks > 1 && ctx->opt("p2p", "1") == "1") setup_p2p(p.get());
+  if (ctx->nranks > 1 && !p->p2p) ctx->nccl_halo_in_use = true;
   *out = p.release();
   API_END(ctx)
 }

@@ -86,6 +86,7 @@ struct gsb_ctx_s {
   // next inner solve, so that a maxiter=1 GMG preconditioner need not synchronise to decide `done`
   const double *hint_vec = nullptr;
   double hint_norm = 0.0;
+  bool nccl_halo_in_use = false;  // some plan fell back to (or was asked to use) ncclSend/ncclRecv
   // optional per-launch profiling of the row kernels (bench.py's roofline numbers)
   struct ProfRec { int mode; int stream; int64_t nrows, nnz; cudaEvent_t e0, e1; };
   bool profiling = false;

@@ -263,7 +263,7 @@ struct GMGNS : gsb_solver_s {
       // (multi-rank: NCCL collectives are capturable and the peer-memory halo exchange keeps its
       //  sequence number on the device, so the replay is valid there too; the two-stream overlap is not)
       const bool use_graph = !ctx->profiling && ctx->opt("graph", "1") == "1" &&
-                             (ctx->nranks == 1 || (ctx->opt("p2p", "1") == "1" && ctx->opt("overlap", "0") != "1"));
+                             (ctx->nranks == 1 || (!ctx->nccl_halo_in_use && ctx->opt("overlap", "0") != "1"));
       if (use_graph && graph_exec && graph_x == x.d && graph_b == b.d) {
         GSB_CUDA(cudaGraphLaunch(graph_exec, ctx->stream));
         ctx->launches += graph_launches;

@@ -104,6 +104,15 @@ def main():
         assert dd < 1e-10, dd
         print(f"mgpu_check ok: world={world} cells={ncell} iters={s.log.num_iters} hist_diff={dd:.2e} max_err={err:.2e}", flush=True)
     assert err < 1e-7
+    # 4. the NCCL send/recv exchange (fallback when peer memory cannot be mapped) gives the same bits
+    ctx.set_option("p2p", "0")
+    plan2 = gsb.ExchangePlan(ctx, lp.n_own, lp.n_ghost, lp.nbr_snd, lp.snd_ptrs, lp.snd_ids, lp.nbr_rcv, lp.rcv_ptrs, lp.rcv_ids)
+    A2 = gsb.SparseMatrix(ctx, lp.n_own, lp.n_own, lp.n_ghost, *hh.A[0], plan=plan2)
+    x2, y2 = gsb.allocate_in_domain(A2), gsb.allocate_in_range(A2)
+    x2.set(xg[gid[: lp.n_own]])
+    gsb.mul_(y2, A2, x2)
+    assert np.array_equal(y2.get(), yo), "NCCL halo path differs"
+    ctx.set_option("p2p", "1")
     dist.barrier()
     dist.destroy_process_group()
 

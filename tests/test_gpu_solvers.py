@@ -183,6 +183,25 @@ def test_c2_full_size_properties(gsb, ctx):
     true_res = np.linalg.norm(hh.b - rd.get())
     assert abs(true_res - h[-1]) <= 1e-6 * h[0] * 1e-2
     assert np.max(np.abs(xd.get() - synth.exact_solution(hh.levels[0]))) < 1e-7
+    # the oracle on the SAME assembled system at full size (threaded C kernels: ~3 s): iteration count and
+    # relative residual history within the north-star tolerance
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    ola.set_threaded(True)
+    try:
+        mats, P, R = oracle_hierarchy(hh)
+        smo = [OS.RichardsonSmoother(OS.JacobiLinearSolver(), 10, 2.0 / 3.0)] * 3
+        go = OS.GMGLinearSolver(mats, P, R, pre_smoothers=smo, post_smoothers=smo, maxiter=1)
+        so = OS.CGSolver(go, maxiter=50, atol=1e-14, rtol=1e-8)
+        xo = np.zeros(mats[0].shape[0])
+        OS.solve_(xo, OS.numerical_setup(OS.symbolic_setup(so, mats[0]), mats[0]), hh.b)
+    finally:
+        ola.set_threaded(False)
+    assert s.log.num_iters == so.log.num_iters
+    assert rel_hist_diff(h, so.log.history()) < HIST_TOL
+    assert np.linalg.norm(xd.get() - xo) <= 1e-9 * np.linalg.norm(xo)
     # linearity of the fine-level SpMV: A(2x) == 2 A(x) exactly (power-of-two scaling)
     x2 = dev_vec(gsb, A, 2.0 * xd.get())
     r2 = dev_vec(gsb, A, domain=False)

@@ -26,6 +26,16 @@ def test_abi_exports_every_declared_symbol():
     assert set(gsb200._lib.SIGNATURES) == declared
 
 
+def test_julia_shim_binds_only_declared_symbols():
+    """every `ccall((:gsb_xxx, libgsb), ...)` of the Julia shim names an entry point of include/gsb200.h"""
+    hdr = open(os.path.join(ROOT, "include", "gsb200.h")).read()
+    declared = set(re.findall(r"\b(gsb_[a-z0-9_]+)\s*\(", hdr))
+    jl = open(os.path.join(ROOT, "gridapsolvers.jl_b200", "julia", "GridapSolversB200.jl")).read()
+    used = set(re.findall(r":(gsb_[a-z0-9_]+)", jl))
+    assert len(used) >= 15
+    assert used <= declared, sorted(used - declared)
+
+
 def test_no_cpu_fallback_without_device():
     import torch
 
