@@ -638,6 +638,11 @@ void dense_apply(gsb_ctx_t ctx, const DevBuf<double> &inv_rows, int64_t n_global
 }  // namespace gsb
 
 // ------------------------------------------------------------------------------------------ C ABI
+#define GSB_NULLCHK(h)                                         \
+  if (!(h)) {                                                 \
+    gsb::set_error(nullptr, "NULL handle passed to libgsb200"); \
+    return GSB_EINVAL;                                        \
+  }
 #define API_BEGIN try {
 #define API_END(ctx)                               \
   }                                                \
@@ -739,18 +744,21 @@ int gsb_finalize(gsb_ctx_t ctx) {
 }
 
 int gsb_synchronize(gsb_ctx_t ctx) {
+  GSB_NULLCHK(ctx)
   API_BEGIN
   GSB_CUDA(cudaStreamSynchronize(ctx->stream));
   API_END(ctx)
 }
 
 int gsb_timer_start(gsb_ctx_t ctx) {
+  GSB_NULLCHK(ctx)
   API_BEGIN
   GSB_CUDA(cudaEventRecord(ctx->t0, ctx->stream));
   API_END(ctx)
 }
 
 int gsb_timer_stop(gsb_ctx_t ctx, float *ms) {
+  GSB_NULLCHK(ctx)
   API_BEGIN
   GSB_CUDA(cudaEventRecord(ctx->t1, ctx->stream));
   GSB_CUDA(cudaEventSynchronize(ctx->t1));
@@ -759,11 +767,13 @@ int gsb_timer_stop(gsb_ctx_t ctx, float *ms) {
 }
 
 int gsb_launch_count(gsb_ctx_t ctx, int64_t *out) {
+  GSB_NULLCHK(ctx)
   *out = ctx->launches;
   return GSB_OK;
 }
 
 int gsb_profile_start(gsb_ctx_t ctx) {
+  GSB_NULLCHK(ctx)
   API_BEGIN
   for (auto &r : ctx->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   ctx->prof.clear();
@@ -774,6 +784,7 @@ int gsb_profile_start(gsb_ctx_t ctx) {
 // aggregates the recorded row-kernel launches by (mode, kernel kind, rows, nnz)
 int gsb_profile_stop(gsb_ctx_t ctx, int cap, int *n_out, int *mode, int *stream, int64_t *nrows, int64_t *nnz,
                      int *count, double *total_ms) {
+  GSB_NULLCHK(ctx)
   API_BEGIN
   ctx->profiling = false;
   GSB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -801,6 +812,7 @@ int gsb_profile_stop(gsb_ctx_t ctx, int cap, int *n_out, int *mode, int *stream,
 
 // diagnostics: time `reps` back-to-back launches of one row-kernel mode on scratch vectors
 int gsb_bench_rows(gsb_mat_t A, int mode, int reps, float *avg_ms) {
+  GSB_NULLCHK(A)
   API_BEGIN
   gsb_ctx_t ctx = A->ctx;
   GSB_CHECK(A->nb == 0 && reps >= 1, "bench_rows: bad arguments");
@@ -837,6 +849,7 @@ int gsb_bench_rows(gsb_mat_t A, int mode, int reps, float *avg_ms) {
 }
 
 int gsb_set_option(gsb_ctx_t ctx, const char *key, const char *value) {
+  GSB_NULLCHK(ctx)
   API_BEGIN
   ctx->opts[key] = value;
   API_END(ctx)
@@ -955,6 +968,7 @@ static void setup_p2p(gsb_plan_s *p) {
 int gsb_plan_create(gsb_ctx_t ctx, int64_t n_own, int64_t n_ghost, int n_nbr_snd, const int32_t *nbr_snd,
                     const int64_t *snd_ptrs, const int64_t *snd_local_ids, int n_nbr_rcv, const int32_t *nbr_rcv,
                     const int64_t *rcv_ptrs, const int64_t *rcv_local_ids, int index_base, gsb_plan_t *out) {
+  GSB_NULLCHK(ctx)
   API_BEGIN
   std::unique_ptr<gsb_plan_s> p(new gsb_plan_s());
   p->ctx = ctx; p->n_own = n_own; p->n_ghost = n_ghost;
@@ -1109,6 +1123,7 @@ static void finish_matrix(gsb_mat_s *A, const std::vector<int> &rowptr, const st
 int gsb_mat_create(gsb_ctx_t ctx, int64_t n_rows, int64_t n_own_cols, int64_t n_ghost_cols, int fmt, int index_base,
                    int index_bytes, const void *ptr, const void *idx, const double *vals, gsb_plan_t plan,
                    gsb_mat_t *out) {
+  GSB_NULLCHK(ctx)
   API_BEGIN
   GSB_CHECK(index_bytes == 4 || index_bytes == 8, "mat: index_bytes must be 4 or 8");
   GSB_CHECK(fmt == GSB_FMT_CSR || fmt == GSB_FMT_CSC, "mat: unknown format");
@@ -1172,6 +1187,7 @@ int gsb_mat_create(gsb_ctx_t ctx, int64_t n_rows, int64_t n_own_cols, int64_t n_
 }
 
 int gsb_mat_update_values(gsb_mat_t A, const double *vals) {
+  GSB_NULLCHK(A)
   API_BEGIN
   GSB_CHECK(A->nb == 0, "update_values: block matrix");
   std::vector<double> v((size_t)A->nnz);
@@ -1192,6 +1208,7 @@ int gsb_mat_update_values(gsb_mat_t A, const double *vals) {
 }
 
 int gsb_mat_info(gsb_mat_t A, int64_t *n_rows, int64_t *n_own_cols, int64_t *n_ghost_cols, int64_t *nnz) {
+  GSB_NULLCHK(A)
   if (n_rows) *n_rows = A->n_rows;
   if (n_own_cols) *n_own_cols = A->n_own_cols;
   if (n_ghost_cols) *n_ghost_cols = A->n_ghost_cols;
@@ -1205,6 +1222,7 @@ int gsb_mat_destroy(gsb_mat_t A) {
 }
 
 int gsb_block_mat_create(gsb_ctx_t ctx, int nb, const gsb_mat_t *blocks, gsb_mat_t *out) {
+  GSB_NULLCHK(ctx)
   API_BEGIN
   GSB_CHECK(nb >= 1, "block matrix: nb < 1");
   std::unique_ptr<gsb_mat_s> A(new gsb_mat_s());
@@ -1234,6 +1252,7 @@ int gsb_block_mat_create(gsb_ctx_t ctx, int nb, const gsb_mat_t *blocks, gsb_mat
 
 // ---------------------------------------------------------------- vectors
 int gsb_vec_create(gsb_ctx_t ctx, int64_t n_own, int64_t n_ghost, gsb_vec_t *out) {
+  GSB_NULLCHK(ctx)
   API_BEGIN
   GSB_CHECK(n_own >= 0 && n_ghost >= 0, "vec: negative size");
   std::unique_ptr<gsb_vec_s> v(new gsb_vec_s());
@@ -1243,18 +1262,22 @@ int gsb_vec_create(gsb_ctx_t ctx, int64_t n_own, int64_t n_ghost, gsb_vec_t *out
   *out = v.release();
   API_END(ctx)
 }
-int gsb_vec_create_domain(gsb_mat_t A, gsb_vec_t *out) { return gsb_vec_create(A->ctx, A->n_own_cols, A->n_ghost_cols, out); }
-int gsb_vec_create_range(gsb_mat_t A, gsb_vec_t *out) { return gsb_vec_create(A->ctx, A->n_rows, 0, out); }
+int gsb_vec_create_domain(gsb_mat_t A, gsb_vec_t *out) {
+  GSB_NULLCHK(A) return gsb_vec_create(A->ctx, A->n_own_cols, A->n_ghost_cols, out); }
+int gsb_vec_create_range(gsb_mat_t A, gsb_vec_t *out) {
+  GSB_NULLCHK(A) return gsb_vec_create(A->ctx, A->n_rows, 0, out); }
 int gsb_vec_destroy(gsb_vec_t v) {
   delete v;
   return GSB_OK;
 }
 int gsb_vec_size(gsb_vec_t v, int64_t *n_own, int64_t *n_ghost) {
+  GSB_NULLCHK(v)
   if (n_own) *n_own = v->n_own;
   if (n_ghost) *n_ghost = v->n_ghost;
   return GSB_OK;
 }
 int gsb_vec_set(gsb_vec_t v, const double *host, int64_t n) {
+  GSB_NULLCHK(v)
   API_BEGIN
   GSB_CHECK(n == v->n_own, "vec_set: length != own size");
   if (n) GSB_CUDA(cudaMemcpyAsync(v->d, host, sizeof(double) * n, cudaMemcpyHostToDevice, v->ctx->stream));
@@ -1262,6 +1285,7 @@ int gsb_vec_set(gsb_vec_t v, const double *host, int64_t n) {
   API_END(v->ctx)
 }
 int gsb_vec_get(gsb_vec_t v, double *host, int64_t n) {
+  GSB_NULLCHK(v)
   API_BEGIN
   GSB_CHECK(n == v->n_own, "vec_get: length != own size");
   if (n) GSB_CUDA(cudaMemcpyAsync(host, v->d, sizeof(double) * n, cudaMemcpyDeviceToHost, v->ctx->stream));
@@ -1269,6 +1293,7 @@ int gsb_vec_get(gsb_vec_t v, double *host, int64_t n) {
   API_END(v->ctx)
 }
 int gsb_vec_get_local(gsb_vec_t v, double *host, int64_t n) {
+  GSB_NULLCHK(v)
   API_BEGIN
   GSB_CHECK(n == v->n_local(), "vec_get_local: length != local size");
   if (n) GSB_CUDA(cudaMemcpyAsync(host, v->d, sizeof(double) * n, cudaMemcpyDeviceToHost, v->ctx->stream));
@@ -1276,16 +1301,19 @@ int gsb_vec_get_local(gsb_vec_t v, double *host, int64_t n) {
   API_END(v->ctx)
 }
 int gsb_vec_fill(gsb_vec_t v, double value) {
+  GSB_NULLCHK(v)
   API_BEGIN
   gsb::vec_fill(*v, value);
   API_END(v->ctx)
 }
 int gsb_vec_copy(gsb_vec_t dst, gsb_vec_t src) {
+  GSB_NULLCHK(dst)
   API_BEGIN
   gsb::vec_copy(*dst, *src);
   API_END(dst->ctx)
 }
 int gsb_vec_consistent(gsb_vec_t v, gsb_plan_t plan) {
+  GSB_NULLCHK(v)
   API_BEGIN
   gsb::consistent(*v, plan);
   GSB_CUDA(cudaStreamSynchronize(v->ctx->stream));
@@ -1294,23 +1322,27 @@ int gsb_vec_consistent(gsb_vec_t v, gsb_plan_t plan) {
 
 // ---------------------------------------------------------------- primitives
 int gsb_spmv(gsb_mat_t A, gsb_vec_t x, gsb_vec_t y, double alpha, double beta) {
+  GSB_NULLCHK(A)
   API_BEGIN
   gsb::spmv(A, *x, *y, alpha, beta);
   API_END(A->ctx)
 }
 int gsb_dot(gsb_vec_t a, gsb_vec_t b, double *out) {
+  GSB_NULLCHK(a)
   API_BEGIN
   gsb::dot(*a, *b, 0);
   *out = a->ctx->read_scalar(0);
   API_END(a->ctx)
 }
 int gsb_norm2(gsb_vec_t a, double *out) {
+  GSB_NULLCHK(a)
   API_BEGIN
   gsb::dot(*a, *a, 0);
   *out = std::sqrt(a->ctx->read_scalar(0));
   API_END(a->ctx)
 }
 int gsb_axpby(gsb_vec_t z, double alpha, gsb_vec_t x, double beta, gsb_vec_t y) {
+  GSB_NULLCHK(z)
   API_BEGIN
   gsb::ew_axpby(*z, gsb::imm(alpha), *x, gsb::imm(beta), y);
   API_END(z->ctx)

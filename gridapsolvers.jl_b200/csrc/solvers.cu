@@ -12,6 +12,11 @@ int set_error(gsb_ctx_t ctx, const std::string &msg);
 }
 using namespace gsb;
 
+#define GSB_NULLCHK(h)                                         \
+  if (!(h)) {                                                 \
+    gsb::set_error(nullptr, "NULL handle passed to libgsb200"); \
+    return GSB_EINVAL;                                        \
+  }
 #define API_BEGIN try {
 #define API_END(ctx)                  \
   }                                   \
@@ -745,6 +750,7 @@ struct SchurNS : gsb_solver_s {
 extern "C" {
 
 int gsb_identity_create(gsb_ctx_t ctx, gsb_solver_t *out) {
+  GSB_NULLCHK(ctx)
   API_BEGIN
   auto *s = new IdentityNS();
   s->ctx = ctx;
@@ -752,22 +758,26 @@ int gsb_identity_create(gsb_ctx_t ctx, gsb_solver_t *out) {
   API_END(ctx)
 }
 int gsb_jacobi_create(gsb_mat_t A, gsb_solver_t *out) {
+  GSB_NULLCHK(A)
   API_BEGIN
   *out = new JacobiNS(A);
   API_END(A->ctx)
 }
 int gsb_richardson_create(gsb_mat_t A, gsb_solver_t M, int niter, double omega, gsb_solver_t *out) {
+  GSB_NULLCHK(A)
   API_BEGIN
   GSB_CHECK(M != nullptr, "Richardson: inner solver is NULL");
   *out = new RichardsonNS(A, M, niter, omega);
   API_END(A->ctx)
 }
 int gsb_from_smoother_create(gsb_mat_t A, gsb_solver_t smoother, gsb_solver_t *out) {
+  GSB_NULLCHK(A)
   API_BEGIN
   *out = new FromSmootherNS(A, smoother);
   API_END(A->ctx)
 }
 int gsb_dense_lu_create(gsb_mat_t A, gsb_solver_t *out) {
+  GSB_NULLCHK(A)
   API_BEGIN
   *out = new DenseLUNS(A);
   API_END(A->ctx)
@@ -775,34 +785,40 @@ int gsb_dense_lu_create(gsb_mat_t A, gsb_solver_t *out) {
 int gsb_gmg_create(gsb_ctx_t ctx, int nlev, const gsb_mat_t *mats, const gsb_mat_t *interp, const gsb_mat_t *restrict_,
                    const gsb_solver_t *pre, const gsb_solver_t *post, gsb_solver_t coarsest, int mode, int cycle_type,
                    int maxiter, double atol, double rtol, gsb_solver_t *out) {
+  GSB_NULLCHK(ctx)
   API_BEGIN
   *out = new GMGNS(ctx, nlev, mats, interp, restrict_, pre, post, coarsest, mode, cycle_type, maxiter, atol, rtol);
   API_END(ctx)
 }
 int gsb_cg_create(gsb_mat_t A, gsb_solver_t Pl, int flexible, int maxiter, double atol, double rtol, gsb_solver_t *out) {
+  GSB_NULLCHK(A)
   API_BEGIN
   *out = new CGNS(A, Pl, flexible != 0, maxiter, atol, rtol);
   API_END(A->ctx)
 }
 int gsb_gmres_create(gsb_mat_t A, gsb_solver_t Pr, gsb_solver_t Pl, int m, int restart, int m_add, int maxiter,
                      double atol, double rtol, gsb_solver_t *out) {
+  GSB_NULLCHK(A)
   API_BEGIN
   *out = new GMRESNS(A, Pr, Pl, m, restart != 0, m_add, false, maxiter, atol, rtol);
   API_END(A->ctx)
 }
 int gsb_fgmres_create(gsb_mat_t A, gsb_solver_t Pr, gsb_solver_t Pl, int m, int restart, int m_add, int maxiter,
                       double atol, double rtol, gsb_solver_t *out) {
+  GSB_NULLCHK(A)
   API_BEGIN
   *out = new GMRESNS(A, Pr, Pl, m, restart != 0, m_add, true, maxiter, atol, rtol);
   API_END(A->ctx)
 }
 int gsb_minres_create(gsb_mat_t A, gsb_solver_t Pl, int maxiter, double atol, double rtol, gsb_solver_t *out) {
+  GSB_NULLCHK(A)
   API_BEGIN
   *out = new MINRESNS(A, Pl, maxiter, atol, rtol);
   API_END(A->ctx)
 }
 int gsb_block_solver_create(gsb_ctx_t ctx, int nb, const gsb_mat_t *blocks, const gsb_solver_t *solvers,
                             const double *coeffs, int half, int diagonal, gsb_solver_t *out) {
+  GSB_NULLCHK(ctx)
   API_BEGIN
   *out = new BlockNS(ctx, nb, blocks, solvers, coeffs, half, diagonal != 0);
   API_END(ctx)
@@ -810,18 +826,21 @@ int gsb_block_solver_create(gsb_ctx_t ctx, int nb, const gsb_mat_t *blocks, cons
 
 int gsb_richardson_linear_create(gsb_mat_t A, gsb_solver_t Pl, double omega, int maxiter, double atol, double rtol,
                                  gsb_solver_t *out) {
+  GSB_NULLCHK(A)
   API_BEGIN
   *out = new RichardsonLinearNS(A, Pl, omega, maxiter, atol, rtol);
   API_END(A->ctx)
 }
 int gsb_schur_complement_create(gsb_ctx_t ctx, gsb_solver_t A_ns, gsb_mat_t B, gsb_mat_t C, gsb_solver_t S_ns,
                                 gsb_solver_t *out) {
+  GSB_NULLCHK(ctx)
   API_BEGIN
   GSB_CHECK(A_ns && S_ns && B && C, "Schur complement: NULL argument");
   *out = new SchurNS(ctx, A_ns, B, C, S_ns);
   API_END(ctx)
 }
 int gsb_cg_record_coefficients(gsb_solver_t ns, int enable) {
+  GSB_NULLCHK(ns)
   API_BEGIN
   CGNS *cg = dynamic_cast<CGNS *>(ns);
   GSB_CHECK(cg != nullptr, "not a CG numerical setup");
@@ -829,6 +848,7 @@ int gsb_cg_record_coefficients(gsb_solver_t ns, int enable) {
   API_END(ns->ctx)
 }
 int gsb_cg_coefficients(gsb_solver_t ns, double *alpha, double *beta, int64_t cap, int64_t *n) {
+  GSB_NULLCHK(ns)
   API_BEGIN
   CGNS *cg = dynamic_cast<CGNS *>(ns);
   GSB_CHECK(cg != nullptr, "not a CG numerical setup");
@@ -838,17 +858,20 @@ int gsb_cg_coefficients(gsb_solver_t ns, double *alpha, double *beta, int64_t ca
 }
 
 int gsb_solver_update(gsb_solver_t ns, gsb_mat_t A) {
+  GSB_NULLCHK(ns)
   API_BEGIN
   ns->update(A);
   API_END(ns->ctx)
 }
 int gsb_solve(gsb_solver_t ns, gsb_vec_t x, gsb_vec_t b) {
+  GSB_NULLCHK(ns)
   API_BEGIN
   ns->solve(*x, *b);
   GSB_CUDA(cudaStreamSynchronize(ns->ctx->stream));
   API_END(ns->ctx)
 }
 int gsb_solve_host(gsb_solver_t ns, double *x_host, const double *b_host, int64_t n) {
+  GSB_NULLCHK(ns)
   API_BEGIN
   gsb_ctx_t ctx = ns->ctx;
   // staging vectors sized like the caller's own values; ghost room is taken from the solver's
@@ -868,6 +891,7 @@ int gsb_solve_host(gsb_solver_t ns, double *x_host, const double *b_host, int64_
   API_END(ns->ctx)
 }
 int gsb_solver_log(gsb_solver_t ns, int *num_iters, double *residuals, int64_t cap, int *flag) {
+  GSB_NULLCHK(ns)
   API_BEGIN
   GSB_CHECK(ns->has_log, std::string(ns->name()) + " has no convergence log");
   ns->finish();

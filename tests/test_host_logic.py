@@ -36,6 +36,21 @@ def test_julia_shim_binds_only_declared_symbols():
     assert used <= declared, sorted(used - declared)
 
 
+def test_null_handles_are_errors_not_crashes():
+    """every entry point rejects a NULL first handle with GSB_EINVAL and a message (no device needed)"""
+    L = gsb200._lib.lib()
+    n = ctypes.c_int64()
+    d = ctypes.c_double()
+    assert L.gsb_vec_fill(None, 1.0) == 1
+    assert b"NULL handle" in L.gsb_last_error(None)
+    assert L.gsb_spmv(None, None, None, 1.0, 0.0) == 1
+    assert L.gsb_solve(None, None, None) == 1
+    assert L.gsb_mat_info(None, ctypes.byref(n), None, None, None) == 1
+    assert L.gsb_dot(None, None, ctypes.byref(d)) == 1
+    assert L.gsb_solver_log(None, None, None, 0, None) == 1
+    assert L.gsb_mat_destroy(None) == 0 and L.gsb_solver_destroy(None) == 0  # destroying NULL is a no-op
+
+
 def test_no_cpu_fallback_without_device():
     import torch
 
