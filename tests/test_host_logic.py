@@ -199,3 +199,93 @@ def test_two_rank_gloo_halo_spmv_and_dot():
         y[gid] = yl
         assert abs(d - float(xg @ yg)) <= 1e-12 * abs(float(xg @ yg)) + 1e-12
     assert np.abs(y - yg).max() < 1e-13
+
+
+def _gloo_pcg_worker(rank, world, nc, parts, port, q):
+    """Jacobi-preconditioned CG over a 2-part PartitionedArrays-style distribution, numpy local kernels,
+    gloo for consistent! and the dot all-reduces: the same statement sequence as CGSolvers.jl:73-120."""
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lp = synth.make_level_part(nc, parts, rank)
+        rp, col, val, b = synth.poisson_rows(lp)
+        A = synth.to_scipy(rp, col, val, lp.n_own + lp.n_ghost)
+        n = lp.n_own
+
+        def consistent(v):
+            reqs, bufs = [], []
+            for k, qn in enumerate(lp.nbr_rcv):
+                buf = torch.zeros(int(lp.rcv_ptrs[k + 1] - lp.rcv_ptrs[k]), dtype=torch.float64)
+                bufs.append(buf)
+                reqs.append(dist.irecv(buf, src=int(qn)))
+            for k, qn in enumerate(lp.nbr_snd):
+                reqs.append(dist.isend(torch.from_numpy(v[lp.snd_ids[lp.snd_ptrs[k]:lp.snd_ptrs[k + 1]]].copy()), dst=int(qn)))
+            for r in reqs:
+                r.wait()
+            for k, buf in enumerate(bufs):
+                v[lp.rcv_ids[lp.rcv_ptrs[k]:lp.rcv_ptrs[k + 1]]] = buf.numpy()
+
+        def pdot(a, c):
+            t = torch.tensor([float(np.dot(a[:n], c[:n]))], dtype=torch.float64)
+            dist.all_reduce(t)
+            return float(t.item())
+
+        def mul(v):  # mul!(w,A,v): halo of v, then the local rows
+            consistent(v)
+            return A @ v
+
+        inv_diag = 1.0 / A.diagonal()[:n]  # own-own block diagonal (JacobiLinearSolvers.jl:29-34)
+        nl = lp.n_own + lp.n_ghost
+        x, p, z, r, w = (np.zeros(nl) for _ in range(5))
+        r[:n] = b - mul(x)
+        gamma, hist = 1.0, [np.sqrt(pdot(r, r))]
+        for _ in range(200):
+            z[:n] = inv_diag * r[:n]
+            beta = gamma
+            gamma = pdot(z, r)
+            beta = gamma / beta
+            p[:n] = z[:n] + beta * p[:n]
+            w[:n] = mul(p)
+            alpha = gamma / pdot(p, w)
+            x[:n] += alpha * p[:n]
+            r[:n] -= alpha * w[:n]
+            hist.append(np.sqrt(pdot(r, r)))
+            if hist[-1] / hist[0] < 1e-8:
+                break
+        q.put((rank, synth.lexicographic_ids(lp)[:n], x[:n].copy(), hist))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_distributed_pcg_matches_serial_oracle():
+    import torch.multiprocessing as mp
+
+    from oracle import linalg as ola
+    from oracle import solvers as OS
+
+    nc, parts = (8, 8, 16), (1, 1, 2)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_pcg_worker, args=(r, 2, nc, parts, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    sysm = fem.poisson(nc)
+    Ao = ola.CSR(sysm.A)
+    s = OS.CGSolver(OS.JacobiLinearSolver(), maxiter=200, atol=0.0, rtol=1e-8)
+    xo = np.zeros(Ao.shape[0])
+    OS.solve_(xo, OS.numerical_setup(OS.symbolic_setup(s, Ao), Ao), sysm.b)
+    x = np.zeros(Ao.shape[0])
+    for rank, gid, xl, hist in res:
+        x[gid] = xl
+        assert len(hist) - 1 == s.log.num_iters
+        assert np.max(np.abs(np.array(hist) - s.log.history())) <= 1e-10 * hist[0]
+    assert np.linalg.norm(x - xo) <= 1e-9 * np.linalg.norm(xo)
