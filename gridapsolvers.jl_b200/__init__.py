@@ -11,4 +11,5 @@ from .api import (Context, ExchangePlan, SparseMatrix, BlockSparseMatrix, Vector
                   numerical_setup, numerical_setup_, solve_, ldiv_, IdentitySolver, JacobiLinearSolver, LUSolver,
                   RichardsonSmoother, LinearSolverFromSmoother, Fill, GMGLinearSolver, CGSolver, GMRESSolver,
                   FGMRESSolver, MINRESSolver, BlockTriangularSolver, BlockDiagonalSolver, LanczosDiagnostic,
-                  RichardsonLinearSolver, SchurComplementSolver)
+                  RichardsonLinearSolver, SchurComplementSolver, HierarchicalArray, num_levels, with_level,
+                  get_solver_tolerances, set_solver_tolerances_)

@@ -315,11 +315,63 @@ class ConvergenceLog:
         self.residuals[:] = 0.0
         check(_lib.lib().gsb_solver_log(handle, ctypes.byref(n), _ptr(self.residuals), self.residuals.shape[0], ctypes.byref(flag)))
         self.num_iters, self.flag = n.value, flag.value
+        if self.verbose > 1:  # ConvergenceLogs.jl:103-109,121-126 (printed after the device solve returns)
+            t = " " * (2 + 2 * self.depth)
+            print(" " * (2 * self.depth) + (("-" * 15) + f" Starting {self.name} solver ").ljust(55, "-"))
+            r0 = self.residuals[0]
+            for k in range(self.num_iters + 1):
+                r = self.residuals[k]
+                print(t + "> Iteration %3i - Residuals: %.2e,   %.2e " % (k, r, (r / r0) if (k and r0) else 1))
         if self.verbose > 0:  # ConvergenceLogs.jl:139-148
             t = " " * (2 * self.depth)
             r = self.residuals[self.num_iters]
             print(f"{t}Solver {self.name} finished with reason {self.flag}")
             print(t + "Iterations: %3i - Residuals: %.2e,   %.2e " % (self.num_iters, r, r / self.residuals[0] if self.residuals[0] else float('nan')))
+
+
+def get_solver_tolerances(solver) -> SolverTolerances:
+    """SolverTolerances.jl:51-56"""
+    return solver.log.tols
+
+
+def set_solver_tolerances_(solver, maxiter=1000, atol=np.finfo(np.float64).eps, rtol=1e-5, dtol=math.inf):
+    """set_solver_tolerances!(s; maxiter, atol, rtol, dtol) -- SolverTolerances.jl:58-84 (takes effect at the next
+    numerical_setup, which is when the device-side NumericalSetup copies the tolerances)."""
+    t = solver.log.tols
+    t.maxiter, t.atol, t.rtol, t.dtol = int(maxiter), float(atol), float(rtol), float(dtol)
+    solver.log.residuals = np.zeros(t.maxiter + 1)
+    return t
+
+
+class HierarchicalArray:
+    """MultilevelTools/HierarchicalArrays.jl:13-22: one entry per level plus the ranks taking part in it.  In this
+    build every level lives on every rank (no level redistribution yet), so `with_level` always runs `f`."""
+
+    def __init__(self, array, ranks=None):
+        self.array = list(array)
+        self.ranks = list(ranks) if ranks is not None else [None] * len(self.array)
+
+    def __len__(self):
+        return len(self.array)
+
+    def __getitem__(self, i):
+        return self.array[i]
+
+    def __setitem__(self, i, v):
+        self.array[i] = v
+
+    def __iter__(self):
+        return iter(self.array)
+
+
+def num_levels(a) -> int:  # HierarchicalArrays.jl:71
+    return len(a)
+
+
+def with_level(f, a, lev, default=None):  # HierarchicalArrays.jl:139-149 (1-based level like the reference)
+    if lev < 1 or lev > len(a) or a[lev - 1] is None:
+        return default
+    return f(a[lev - 1])
 
 
 # --------------------------------------------------------------------------- setup protocol
@@ -462,9 +514,11 @@ class GMGLinearSolver(LinearSolver):
         if post_smoothers is None:
             post_smoothers = pre_smoothers
         assert n - 1 == len(interp) == len(restrict) == len(pre_smoothers) == len(post_smoothers)  # @check :59
+        same_smoothers = pre_smoothers is post_smoothers
         assert mode in _MODES and cycle_type in _CYCLES  # @check :60-61
         self.smatrices, self.interp, self.restrict = list(smatrices), list(interp), list(restrict)
-        self.pre_smoothers, self.post_smoothers = pre_smoothers, post_smoothers
+        self.pre_smoothers = list(pre_smoothers)
+        self.post_smoothers = self.pre_smoothers if same_smoothers else list(post_smoothers)
         self.coarsest_solver = coarsest_solver if coarsest_solver is not None else LUSolver()
         self.mode, self.cycle_type = mode, cycle_type
         self.log = ConvergenceLog("GMG", SolverTolerances(maxiter=maxiter, atol=atol, rtol=rtol), verbose=verbose)

@@ -158,6 +158,24 @@ function device_ns(s::LinearSolvers.MINRESSolver, A::B200Matrix, reg)
   h = _create(:gsb_minres_create, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cdouble, Cdouble), A.h, _h(Pl), t.maxiter, t.atol, t.rtol)
   push!(reg, (s.log, h)); h
 end
+function device_ns(s::LinearSolvers.RichardsonLinearSolver, A::B200Matrix, reg)
+  s.ω isa Float64 || error("RichardsonLinearSolver: only a scalar relaxation parameter is mirrored")
+  Pl = device_ns(s.Pl, A, reg); t = s.log.tols
+  h = _create(:gsb_richardson_linear_create, (Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint, Cdouble, Cdouble), A.h, _h(Pl), s.ω, t.maxiter, t.atol, t.rtol)
+  push!(reg, (s.log, h)); h
+end
+"""
+BlockTriangularSolver with `LinearSystemBlock`s (src/BlockSolvers/BlockTriangularSolvers.jl:26-58): `blocks` is the
+matrix of B200Matrix blocks of the system (nothing = zero block); diagonal solvers act on blocks[i,i].
+"""
+function device_block_triangular(ctx::B200Context, blocks::Matrix, solvers::Vector, coeffs::Matrix{Float64}, half::Symbol, reg)
+  nb = length(solvers)
+  hs = Ptr{Cvoid}[device_ns(solvers[i], blocks[i,i], reg) for i in 1:nb]
+  hb = Ptr{Cvoid}[isnothing(blocks[i,j]) ? C_NULL : blocks[i,j].h for i in 1:nb for j in 1:nb]   # row-major
+  cf = Float64[coeffs[i,j] for i in 1:nb for j in 1:nb]
+  _create(:gsb_block_solver_create, (Ptr{Cvoid}, Cint, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{Float64}, Cint, Cint),
+          ctx.h, nb, hb, hs, cf, half == :lower ? 1 : 0, 0)
+end
 """
 GMGLinearSolverFromMatrices (src/LinearSolvers/GMGLinearSolvers.jl:8-18).  `interp[l]` / `restrict[l]`
 must be explicit sparse matrices (legal for the reference: GMG only calls mul! on them, :484,491);

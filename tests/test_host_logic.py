@@ -289,3 +289,41 @@ def test_two_rank_gloo_distributed_pcg_matches_serial_oracle():
         assert len(hist) - 1 == s.log.num_iters
         assert np.max(np.abs(np.array(hist) - s.log.history())) <= 1e-10 * hist[0]
     assert np.linalg.norm(x - xo) <= 1e-9 * np.linalg.norm(xo)
+
+
+def test_host_mirror_plumbing():
+    """HierarchicalArray / with_level / tolerances: host-only pieces of the reference interface"""
+    h = gsb200.HierarchicalArray(["A1", "A2", None])
+    assert gsb200.num_levels(h) == 3 and h[1] == "A2"
+    assert gsb200.with_level(lambda a: a + "!", h, 1) == "A1!"
+    assert gsb200.with_level(lambda a: a, h, 3, default="skip") == "skip"  # rank not in the level
+    s = gsb200.CGSolver(maxiter=7)
+    assert s.log.residuals.shape[0] == 8 and gsb200.get_solver_tolerances(s).maxiter == 7
+    gsb200.set_solver_tolerances_(s, maxiter=12, rtol=1e-9)
+    assert s.log.tols.maxiter == 12 and s.log.tols.rtol == 1e-9 and s.log.residuals.shape[0] == 13
+    # Fill shares ONE smoother object; pre is post => shared caches (GMGLinearSolvers.jl:52,190-194)
+    sm = gsb200.Fill(gsb200.RichardsonSmoother(gsb200.JacobiLinearSolver(), 10, 2.0 / 3.0), 2)
+    assert sm[0] is sm[1]
+    g = gsb200.GMGLinearSolver(gsb200.HierarchicalArray([1, 2, 3]), [1, 2], [1, 2], pre_smoothers=sm, post_smoothers=sm)
+    assert g.pre_smoothers is g.post_smoothers and g.log.tols.maxiter == 100 and g.log.tols.rtol == 1e-8
+    with pytest.raises(AssertionError):
+        gsb200.GMGLinearSolver([1, 2, 3], [1], [1, 2])
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (CPU oracle port) prints one JSON line with the contract's keys"""
+    import json
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cells-per-gpu", "16"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["value"] > 0 and d["dtype"] == "f64" and d["vs_baseline"] is None
