@@ -99,7 +99,7 @@ class Context:
         check(_lib.lib().gsb_profile_stop(self.h, cap, ctypes.byref(n), _ptr(mode), _ptr(st), _ptr(nrows), _ptr(nnz),
                                           _ptr(cnt), _ptr(ms)))
         names = {0: "spmv", 1: "residual", 2: "sweep", 3: "spmv_dot", 4: "spmv_add", 5: "sweeps_pipelined"}
-        impl = {0: "csr_vector", 1: "csr_tma_stream", 2: "sell32"}
+        impl = {0: "csr_vector", 1: "csr_tma_stream", 2: "sell32", 3: "sell32_xstage"}
         return [dict(mode=names[int(mode[i])], impl=impl.get(int(st[i]), "sell32_l2_pipeline_S%d" % (int(st[i]) - 100)), nrows=int(nrows[i]), nnz=int(nnz[i]),
                      count=int(cnt[i]), total_ms=float(ms[i])) for i in range(n.value)]
 

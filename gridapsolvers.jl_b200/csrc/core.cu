@@ -8,6 +8,7 @@
 
 #include "kernels.cuh"
 #include "ops.h"
+#include "xstage.h"
 
 namespace gsb {
 
@@ -364,6 +365,16 @@ static void launch_rows(gsb_mat_t A, RowArgs &a) {
   } prof_end{ctx, &rec};
   const bool sell = A->sell_ok && (pref == "sell" || (pref == "auto" && A->n_rows >= (int64_t)std::stoll(ctx->opt("sell_min_rows", "1"))));
   rec.stream = sell ? 2 : rec.stream;
+  if (sell && A->xs_ok && ctx->opt("xstage", "0") == "1") {
+    XStageArgs m{A->rowptr.p, A->sell_off.p, A->xs_lcol.p, A->sell_val.p, A->xs_chunk_seg_ptr.p,
+                 A->xs_seg_start.p, A->xs_seg_len.p, A->xs_seg_off.p, A->n_rows};
+    const int64_t grid = (A->n_rows + 255) / 256;
+    if (MODE == ROW_SPMV_DOT) GSB_CHECK((size_t)grid <= PARTIALS_CAP, "matrix too large for the fused dot");
+    csr_sell_xs_kernel<MODE, 256, SELL_U><<<(unsigned)grid, 256, sizeof(double) * (size_t)A->xs_max_window, ctx->stream>>>(m, a);
+    launched(ctx);
+    rec.stream = 3;
+    return;
+  }
   if (sell) {
     launch_sell<MODE>(A, a);
     return;
@@ -810,6 +821,41 @@ int gsb_profile_stop(gsb_ctx_t ctx, int cap, int *n_out, int *mode, int *stream,
   API_END(ctx)
 }
 
+// diagnostics (pure host, no device needed): plan of the staged-x-window kernel for a CSR matrix.
+// out[0] = ok, out[1] = chunks, out[2] = segments, out[3] = max window, out[4] = total window (doubles);
+// lcol_check (optional, nnz entries, CSR order) receives seg_start + (lcol - seg_off) of every entry, i.e. the
+// column the kernel would gather -- it must equal `col`.
+int gsb_diag_xstage_plan(int64_t n_rows, const int *rowptr, const int *col, int chunk_rows, int gap, int cap,
+                         int64_t *out, int *lcol_check) {
+  API_BEGIN
+  GSB_CHECK(rowptr && col && out && chunk_rows >= 32 && chunk_rows % 32 == 0, "xstage plan: bad arguments");
+  const int64_t nsl = (n_rows + 31) / 32;
+  std::vector<int> soff((size_t)nsl + 1, 0);
+  for (int64_t sl = 0; sl < nsl; ++sl) {
+    int w = 0;
+    for (int64_t i = sl * 32; i < std::min<int64_t>(n_rows, sl * 32 + 32); ++i) w = std::max(w, rowptr[i + 1] - rowptr[i]);
+    soff[(size_t)sl + 1] = soff[(size_t)sl] + w;
+  }
+  XStagePlan xp = build_xstage(n_rows, rowptr, col, soff.data(), chunk_rows, gap, cap);
+  out[0] = xp.ok; out[1] = (int64_t)xp.chunk_seg_ptr.size() - 1; out[2] = (int64_t)xp.seg_start.size();
+  out[3] = xp.max_window; out[4] = xp.total_window;
+  if (xp.ok && lcol_check) {
+    for (int64_t i = 0; i < n_rows; ++i) {
+      const int64_t c = i / chunk_rows;
+      const size_t base = ((size_t)soff[(size_t)(i >> 5)] << 5) + (size_t)(i & 31);
+      for (int e = rowptr[i], k = 0; e < rowptr[i + 1]; ++e, ++k) {
+        const int lc = xp.lcol[base + (size_t)k * 32];
+        int found = -1;
+        for (int sg = xp.chunk_seg_ptr[(size_t)c]; sg < xp.chunk_seg_ptr[(size_t)c + 1]; ++sg)
+          if (lc >= xp.seg_off[(size_t)sg] && lc < xp.seg_off[(size_t)sg] + xp.seg_len[(size_t)sg])
+            found = xp.seg_start[(size_t)sg] + (lc - xp.seg_off[(size_t)sg]);
+        lcol_check[e] = found;
+      }
+    }
+  }
+  API_END(nullptr)
+}
+
 // diagnostics: time `reps` back-to-back launches of one row-kernel mode on scratch vectors
 int gsb_bench_rows(gsb_mat_t A, int mode, int reps, float *avg_ms) {
   GSB_NULLCHK(A)
@@ -1080,6 +1126,25 @@ static void finish_matrix(gsb_mat_s *A, const std::vector<int> &rowptr, const st
       A->sell_entries = entries;
       A->sell_ok = true;
       A->h_sell_off = soff;
+    }
+  }
+  // staged-x-window plan (opt-in at matrix creation time)
+  A->xs_ok = false;
+  if (A->sell_ok && ctx->opt("xstage", "0") == "1") {
+    XStagePlan xp = build_xstage(A->n_rows, rowptr.data(), col.data(), A->h_sell_off.data(), 256, 8, 6144);
+    if (xp.ok) {
+      auto up_i = [&](DevBuf<int> &d, const std::vector<int> &h) {
+        d.alloc(std::max<size_t>(1, h.size()));
+        if (!h.empty()) GSB_CUDA(cudaMemcpy(d.p, h.data(), sizeof(int) * h.size(), cudaMemcpyHostToDevice));
+      };
+      up_i(A->xs_chunk_seg_ptr, xp.chunk_seg_ptr);
+      up_i(A->xs_seg_start, xp.seg_start);
+      up_i(A->xs_seg_len, xp.seg_len);
+      up_i(A->xs_seg_off, xp.seg_off);
+      A->xs_lcol.alloc(xp.lcol.size());
+      GSB_CUDA(cudaMemcpy(A->xs_lcol.p, xp.lcol.data(), sizeof(unsigned short) * xp.lcol.size(), cudaMemcpyHostToDevice));
+      A->xs_max_window = xp.max_window;
+      A->xs_ok = true;
     }
   }
   // interior / boundary slice lists (only for matrices with ghost columns)

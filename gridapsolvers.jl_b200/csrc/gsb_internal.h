@@ -155,6 +155,11 @@ struct gsb_mat_s {
   gsb::DevBuf<int> sell_off, sell_col;
   std::vector<int> h_sell_off;
   gsb::DevBuf<double> sell_val;
+  // staged-x-window variant (xstage.h; opt-in, round-2 work item)
+  bool xs_ok = false;
+  int xs_max_window = 0;
+  gsb::DevBuf<unsigned short> xs_lcol;
+  gsb::DevBuf<int> xs_chunk_seg_ptr, xs_seg_start, xs_seg_len, xs_seg_off;
   // L2-pipelined multi-sweep smoother (kernels.cuh sell_pipe_kernel)
   int64_t bw_rows = 0;  // max |col - row| over the own columns
   gsb::DevBuf<unsigned int> pipe_ctr;  // [ticket, exited]

@@ -469,6 +469,94 @@ __global__ void __launch_bounds__(THREADS, 4) sell_pipe_kernel(PipeArgs p) {
 }
 
 // ------------------------------------------------------------------------------------------
+// SELL-32 with a staged x window (opt-in `xstage=1`; planner in xstage.h, NOT yet validated on hardware --
+// round-2 work item 1).  One CTA = one chunk of THREADS rows: the contiguous column segments the chunk
+// references are copied from the gathered vector into shared memory, the per-entry column id is a 16-bit
+// offset into that window, and the row loop gathers from shared memory.  Same accumulation order as
+// csr_sell_kernel (bit-identical results).
+struct XStageArgs {
+  const int *rowptr;
+  const int *slice_off;
+  const unsigned short *lcol;   // SELL layout, window offsets
+  const double *val;            // SELL layout
+  const int *chunk_seg_ptr;     // nchunks + 1
+  const int *seg_start, *seg_len, *seg_off;
+  int64_t nrows;
+};
+__device__ __forceinline__ unsigned short ldg_stream_u16(const unsigned short *p) {
+  unsigned short v;
+  asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
+  return v;
+}
+
+template <int MODE, int THREADS, int U>
+__global__ void __launch_bounds__(THREADS, 4) csr_sell_xs_kernel(XStageArgs m, RowArgs a) {
+  extern __shared__ double xwin[];
+  __shared__ double red_smem[THREADS / 32];
+  const int chunk = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // stage the window: segment after segment, coalesced
+  const int sg0 = m.chunk_seg_ptr[chunk], sg1 = m.chunk_seg_ptr[chunk + 1];
+  for (int sgi = sg0; sgi < sg1; ++sgi) {
+    const int start = m.seg_start[sgi], len = m.seg_len[sgi], off = m.seg_off[sgi];
+    for (int t = threadIdx.x; t < len; t += THREADS) xwin[off + t] = __ldg(a.x + start + t);
+  }
+  __syncthreads();
+  double acc = 0.0;
+  const int64_t slice = (int64_t)chunk * (THREADS / 32) + warp;
+  const int64_t nslices = (m.nrows + 31) >> 5;
+  if (slice < nslices) {
+    const int64_t row = (slice << 5) + lane;
+    const bool valid = row < m.nrows;
+    const int so0 = m.slice_off[slice], so1 = m.slice_off[slice + 1];
+    const int width = so1 - so0;
+    int len = 0;
+    RowPre<MODE> pre{};
+    double s = 0.0;
+    if (valid) {
+      len = m.rowptr[row + 1] - m.rowptr[row];
+      row_prefetch<MODE>(a, row, pre);
+      s = row_init<MODE>(a, row);
+    }
+    const size_t base = ((size_t)so0 << 5) + lane;
+    const unsigned short *cp = m.lcol + base;
+    const double *vp = m.val + base;
+    const double al = a.alpha;
+    int k = 0;
+    for (; k + U <= width; k += U) {
+      unsigned short cc[U];
+      double vv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) cc[u] = ldg_stream_u16(cp + (size_t)(k + u) * 32);
+#pragma unroll
+      for (int u = 0; u < U; ++u) vv[u] = ldg_stream_f64(vp + (size_t)(k + u) * 32);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (k + u < len) {
+          double t = xwin[cc[u]];
+          if (MODE == ROW_SPMV) t = __dmul_rn(t, al);
+          s = __dadd_rn(s, __dmul_rn(vv[u], t));
+        }
+      }
+    }
+    for (; k < width; ++k) {
+      const unsigned short c = ldg_stream_u16(cp + (size_t)k * 32);
+      const double v = ldg_stream_f64(vp + (size_t)k * 32);
+      if (k < len) {
+        double t = xwin[c];
+        if (MODE == ROW_SPMV) t = __dmul_rn(t, al);
+        s = __dadd_rn(s, __dmul_rn(v, t));
+      }
+    }
+    if (valid) row_epilogue_pre<MODE>(a, row, s, pre, acc);
+  }
+  if (MODE == ROW_SPMV_DOT) {
+    double v[1] = {acc};
+    grid_reduce_finish<THREADS, 1>(v, a.red, red_smem);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + TMA 1-D bulk copy (cp.async.bulk, SASS: UBLKCP)
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {

@@ -67,6 +67,11 @@ int gsb_launch_count(gsb_ctx_t ctx, int64_t *out);
 int gsb_profile_start(gsb_ctx_t ctx);
 int gsb_profile_stop(gsb_ctx_t ctx, int cap, int *n_out, int *mode, int *stream_kernel, int64_t *nrows, int64_t *nnz,
                      int *count, double *total_ms);
+/* diagnostics (pure host): plan of the opt-in staged-x-window row kernel for a CSR matrix (int32, 0-based,
+ * ascending columns): out[5] = {ok, chunks, segments, max window, total window}; lcol_check (nnz ints or NULL)
+ * receives the column each entry would gather */
+int gsb_diag_xstage_plan(int64_t n_rows, const int *rowptr, const int *col, int chunk_rows, int gap, int cap,
+                         int64_t *out, int *lcol_check);
 /* diagnostics: average duration of `reps` back-to-back launches of one row-kernel mode on scratch vectors */
 int gsb_bench_rows(gsb_mat_t A, int mode, int reps, float *avg_ms);
 /* runtime knobs, "key=value" (e.g. "spmv=stream", "spmv=vector", "graph=0"); for tests/tuning */

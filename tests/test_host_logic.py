@@ -327,3 +327,25 @@ def test_bench_reference_arm_contract():
         assert k in d, k
     assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
     assert d["value"] > 0 and d["dtype"] == "f64" and d["vs_baseline"] is None
+
+
+@pytest.mark.parametrize("nc", [(40, 40), (16, 16, 16), (24, 20, 12)])
+def test_xstage_plan_covers_every_column(nc):
+    """planner of the opt-in staged-x-window kernel (pure host): every entry's 16-bit window offset maps back to
+    its column; windows are small (a few stencil lines) and the total staged x traffic beats the per-entry gather"""
+    sysm = fem.poisson(nc)
+    A = sysm.A.tocsr()
+    A.sort_indices()
+    rp, col = A.indptr.astype(np.int32), A.indices.astype(np.int32)
+    out = np.zeros(5, dtype=np.int64)
+    back = np.full(A.nnz, -7, dtype=np.int32)
+    L = gsb200._lib.lib()
+    rc = L.gsb_diag_xstage_plan(A.shape[0], rp.ctypes.data, col.ctypes.data, 256, 8, 6144, out.ctypes.data, back.ctypes.data)
+    assert rc == 0 and out[0] == 1
+    assert np.array_equal(back, col)
+    assert out[1] == -(-A.shape[0] // 256)
+    assert out[3] <= 6144
+    assert out[4] * 8 < 0.7 * A.nnz * 8  # staged window bytes < 70 % of the per-entry gather bytes
+    # a window cap that is too small is reported, not silently truncated
+    rc = L.gsb_diag_xstage_plan(A.shape[0], rp.ctypes.data, col.ctypes.data, 256, 8, 64, out.ctypes.data, None)
+    assert rc == 0 and out[0] == 0
