@@ -74,7 +74,12 @@ int gsb_diag_xstage_plan(int64_t n_rows, const int *rowptr, const int *col, int 
                          int64_t *out, int *lcol_check);
 /* diagnostics: average duration of `reps` back-to-back launches of one row-kernel mode on scratch vectors */
 int gsb_bench_rows(gsb_mat_t A, int mode, int reps, float *avg_ms);
-/* runtime knobs, "key=value" (e.g. "spmv=stream", "spmv=vector", "graph=0"); for tests/tuning */
+/* runtime knobs (also read from the environment variable GSB_OPTIONS="k=v,k=v" at gsb_init); for tests/tuning:
+ *   spmv=auto|sell|stream|vector   row-kernel family          stream_kernel=ws|v1   TMA ring kernel flavour
+ *   graph=1|0      CUDA-graph replay of a maxiter=1 GMG      gmg_defer_log=1|0     device-resident GMG log norms
+ *   p2p=1|0        NVLink peer-memory halo (at plan creation) overlap=0|1           two-stream halo overlap
+ *   fuse_smoother=1|0  fused Jacobi-Richardson sweeps         pipe_stages=S         L2-pipelined multi-sweep kernel
+ *   xstage=0|1     staged-x-window SELL kernel (at matrix creation), sell=1|0, *_min_rows thresholds */
 int gsb_set_option(gsb_ctx_t ctx, const char *key, const char *value);
 
 /* ---------------------------------------------------------------- exchange plan
@@ -82,7 +87,10 @@ int gsb_set_option(gsb_ctx_t ctx, const char *key, const char *value);
  * the direction of consistent! (owner -> ghost).  snd_local_ids index OWN entries to pack for
  * each send neighbour, rcv_local_ids index local (>= n_own) ghost entries to fill per receive
  * neighbour.  Replaces: PartitionedArrays consistent!/assemble! caches as read at
- * SolverInterfaces/PAExtras.jl:9-110; call sites GridapExtras.jl:42,56. */
+ * SolverInterfaces/PAExtras.jl:9-110; call sites GridapExtras.jl:42,56.
+ * COLLECTIVE when nranks > 1: every rank must create its plans in the same order (the CUDA-IPC handles of the
+ * peer-memory receive buffers are all-gathered here; if any rank cannot map a peer, all ranks fall back to
+ * ncclSend/ncclRecv for this plan).  Option "p2p=0" (gsb_set_option / GSB_OPTIONS) forces the NCCL path. */
 int gsb_plan_create(gsb_ctx_t ctx, int64_t n_own, int64_t n_ghost, int n_nbr_snd, const int32_t *nbr_snd,
                     const int64_t *snd_ptrs, const int64_t *snd_local_ids, int n_nbr_rcv,
                     const int32_t *nbr_rcv, const int64_t *rcv_ptrs, const int64_t *rcv_local_ids,
