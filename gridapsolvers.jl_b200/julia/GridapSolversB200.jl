@@ -76,25 +76,27 @@ function B200Matrix(ctx::B200Context, A::PSparseMatrix)
   mats  = partition(A)
   rows  = partition(axes(A,1))
   cols  = partition(axes(A,2))
-  map(mats, rows, cols) do Al, ri, ci
+  # consistent! direction (owner -> ghost) = the assembly caches with snd/rcv swapped, exactly as the reference
+  # reads them at src/SolverInterfaces/PAExtras.jl:84-86 ("Reversed caches")
+  nbors_rcv, nbors_snd = assembly_neighbors(cols)
+  lids_rcv, lids_snd   = assembly_local_indices(cols, nbors_rcv, nbors_snd)
+  map(mats, rows, cols, nbors_snd, nbors_rcv, lids_snd, lids_rcv) do Al, ri, ci, nb_snd, nb_rcv, l_snd, l_rcv
     o2l, g2l = own_to_local(ci), ghost_to_local(ci)
     n_own, n_ghost = length(o2l), length(g2l)
-    l2new = zeros(Int, n_own + n_ghost)
+    l2new = zeros(Int, n_own + n_ghost)           # Julia local numbering -> own-first numbering
     l2new[o2l] .= 1:n_own
     l2new[g2l] .= n_own .+ (1:n_ghost)
     Aoo = Al[own_to_local(ri), :]                 # own rows only
     I, J, V = findnz(Aoo)
     B = sparse(I, l2new[J], V, length(own_to_local(ri)), n_own + n_ghost)   # CSC, own-first columns
-    # exchange plan (consistent!: owner -> ghost)
-    cache = PartitionedArrays.assembly_cache(ci) |> reverse
-    nbr_snd, nbr_rcv = Int32.(cache.neighbors_snd .- 1), Int32.(cache.neighbors_rcv .- 1)
-    snd_ptrs, rcv_ptrs = Int64.(cache.local_indices_snd.ptrs), Int64.(cache.local_indices_rcv.ptrs)
-    snd_ids = Int64.(l2new[cache.local_indices_snd.data])
-    rcv_ids = Int64.(l2new[cache.local_indices_rcv.data])
+    snd_ptrs, rcv_ptrs = Int64.(l_snd.ptrs), Int64.(l_rcv.ptrs)
+    snd_ids = Int64.(l2new[l_snd.data])           # own entries to pack, per send neighbour
+    rcv_ids = Int64.(l2new[l_rcv.data])           # ghost entries to fill, per receive neighbour
     plan = Ref{Ptr{Cvoid}}()
     check(ccall((:gsb_plan_create, libgsb), Cint,
       (Ptr{Cvoid}, Int64, Int64, Cint, Ptr{Int32}, Ptr{Int64}, Ptr{Int64}, Cint, Ptr{Int32}, Ptr{Int64}, Ptr{Int64}, Cint, Ref{Ptr{Cvoid}}),
-      ctx.h, n_own, n_ghost, length(nbr_snd), nbr_snd, snd_ptrs, snd_ids, length(nbr_rcv), nbr_rcv, rcv_ptrs, rcv_ids, 1, plan))
+      ctx.h, n_own, n_ghost, length(nb_snd), Int32.(nb_snd .- 1), snd_ptrs, snd_ids,
+      length(nb_rcv), Int32.(nb_rcv .- 1), rcv_ptrs, rcv_ids, 1, plan))
     h = Ref{Ptr{Cvoid}}()
     check(ccall((:gsb_mat_create, libgsb), Cint,
       (Ptr{Cvoid}, Int64, Int64, Int64, Cint, Cint, Cint, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}),
