@@ -185,3 +185,24 @@ def test_schur_complement_solver_is_exact_block_inverse():
     ns.solve(x, y)
     M = sp.bmat([[Au, Bt], [B, D]], format="csr")
     assert np.linalg.norm(M @ np.concatenate(x) - np.concatenate(y)) <= 1e-9 * np.linalg.norm(np.concatenate(y))
+
+
+def test_block_diagonal_solver_known_answer():
+    """test/BlockSolvers/BlockDiagonalSolversTests.jl:45,55,66: ||x - x_direct|| < 1e-8 when GMRES is right-
+    preconditioned by a BlockDiagonalSolver of exact diagonal-block solves on a block-diagonal-dominant system"""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+
+    s1, s2 = fem.poisson((6, 6)), fem.poisson((5, 7))
+    n1, n2 = s1.A.shape[0], s2.A.shape[0]
+    rng = np.random.default_rng(4)
+    C12 = sp.random(n1, n2, density=0.05, random_state=1, format="csr") * 0.05
+    C21 = sp.random(n2, n1, density=0.05, random_state=2, format="csr") * 0.05
+    M = S.BlockMatrix([[ola.CSR(s1.A), ola.CSR(C12)], [ola.CSR(C21), ola.CSR(s2.A)]])
+    bd = S.BlockDiagonalSolver([S.LUSolver(), S.LUSolver()])
+    solver = S.GMRESSolver(10, Pr=S.BlockPrecondAdapter(bd), maxiter=50, atol=1e-14, rtol=1e-12)
+    b = rng.standard_normal(n1 + n2)
+    x = np.zeros(n1 + n2)
+    S.solve_(x, S.numerical_setup(S.symbolic_setup(solver, M), M), b)
+    xd = spla.spsolve(M.to_scipy().tocsc(), b)
+    assert np.linalg.norm(x - xd) < 1e-8
