@@ -7,7 +7,7 @@ from . import _lib
 from ._lib import GSBError, build
 from .api import *  # noqa: F401,F403
 from .api import (Context, ExchangePlan, SparseMatrix, BlockSparseMatrix, Vector, allocate_in_domain, allocate_in_range,
-                  mul_, dot, norm, axpby_, copy_, consistent_, SolverTolerances, ConvergenceLog, symbolic_setup,
+                  mul_, dot, norm, axpby_, copy_, consistent_, assemble_, SolverTolerances, ConvergenceLog, symbolic_setup,
                   numerical_setup, numerical_setup_, solve_, ldiv_, IdentitySolver, JacobiLinearSolver, LUSolver,
                   RichardsonSmoother, LinearSolverFromSmoother, Fill, GMGLinearSolver, CGSolver, GMRESSolver,
                   FGMRESSolver, MINRESSolver, BlockTriangularSolver, BlockDiagonalSolver, LanczosDiagnostic,

@@ -32,7 +32,7 @@ SIGNATURES = {
     "gsb_timer_stop": [c_p, PP(ctypes.c_float)],
     "gsb_launch_count": [c_p, PP(c_i64)],
     "gsb_set_option": [c_p, ctypes.c_char_p, ctypes.c_char_p],
-    "gsb_diag_xstage_plan": [c_i64, c_p, c_p, c_i, c_i, c_i, c_p, c_p],
+    "gsb_diag_sell_plan": [c_i64, c_i64, c_i64, c_p, c_p, c_i, c_i, c_p, c_p, c_p],
     "gsb_bench_rows": [c_p, c_i, c_i, PP(ctypes.c_float)],
     "gsb_profile_start": [c_p],
     "gsb_profile_stop": [c_p, c_i, PP(c_i), c_p, c_p, c_p, c_p, c_p, c_p],
@@ -41,6 +41,7 @@ SIGNATURES = {
     "gsb_mat_create": [c_p, c_i64, c_i64, c_i64, c_i, c_i, c_i, c_p, c_p, c_p, c_p, PP(c_p)],
     "gsb_mat_update_values": [c_p, c_p],
     "gsb_mat_info": [c_p, PP(c_i64), PP(c_i64), PP(c_i64), PP(c_i64)],
+    "gsb_mat_format": [c_p, PP(c_i), PP(c_i), PP(c_i), PP(c_i64), PP(c_i64)],
     "gsb_mat_destroy": [c_p],
     "gsb_block_mat_create": [c_p, c_i, PP(c_p), PP(c_p)],
     "gsb_vec_create": [c_p, c_i64, c_i64, PP(c_p)],
@@ -54,6 +55,9 @@ SIGNATURES = {
     "gsb_vec_fill": [c_p, c_d],
     "gsb_vec_copy": [c_p, c_p],
     "gsb_vec_consistent": [c_p, c_p],
+    "gsb_vec_assemble": [c_p, c_p],
+    "gsb_host_register": [c_p, c_p, c_i64],
+    "gsb_host_unregister": [c_p, c_p],
     "gsb_spmv": [c_p, c_p, c_p, c_d, c_d],
     "gsb_dot": [c_p, c_p, PP(c_d)],
     "gsb_norm2": [c_p, PP(c_d)],
@@ -76,6 +80,7 @@ SIGNATURES = {
     "gsb_solver_update": [c_p, c_p],
     "gsb_solve": [c_p, c_p, c_p],
     "gsb_solve_host": [c_p, c_p, c_p, c_i64],
+    "gsb_solve_host_zero_guess": [c_p, c_p, c_p, c_i64],
     "gsb_solver_log": [c_p, PP(c_i), c_p, c_i64, PP(c_i)],
     "gsb_solver_destroy": [c_p],
 }

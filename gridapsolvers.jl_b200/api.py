@@ -98,10 +98,23 @@ class Context:
         ms = np.zeros(cap)
         check(_lib.lib().gsb_profile_stop(self.h, cap, ctypes.byref(n), _ptr(mode), _ptr(st), _ptr(nrows), _ptr(nnz),
                                           _ptr(cnt), _ptr(ms)))
-        names = {0: "spmv", 1: "residual", 2: "sweep", 3: "spmv_dot", 4: "spmv_add", 5: "sweeps_pipelined"}
-        impl = {0: "csr_vector", 1: "csr_tma_stream", 2: "sell32", 3: "sell32_xstage"}
-        return [dict(mode=names[int(mode[i])], impl=impl.get(int(st[i]), "sell32_l2_pipeline_S%d" % (int(st[i]) - 100)), nrows=int(nrows[i]), nnz=int(nnz[i]),
+        names = {0: "spmv", 1: "residual", 2: "sweep", 3: "spmv_dot", 4: "spmv_add"}
+
+        def impl(k):  # 0 CSR fallback kernel; 2 + 10*block_size (+100 sorted rows) block-SELL-32
+            if k == 0:
+                return "csr_vector"
+            bs = (k % 100 - 2) // 10
+            return "bsell32_%dx%d%s" % (bs, bs, "_sorted" if k >= 100 else "")
+
+        return [dict(mode=names[int(mode[i])], impl=impl(int(st[i])), nrows=int(nrows[i]), nnz=int(nnz[i]),
                      count=int(cnt[i]), total_ms=float(ms[i])) for i in range(n.value)]
+
+    def host_register(self, array: np.ndarray):
+        """page-lock a caller-owned numpy buffer (pinned-speed gsb_solve_host / set / get)"""
+        check(_lib.lib().gsb_host_register(self.h, _ptr(array), array.nbytes))
+
+    def host_unregister(self, array: np.ndarray):
+        check(_lib.lib().gsb_host_unregister(self.h, _ptr(array)))
 
     def close(self):
         if self.h:
@@ -142,6 +155,8 @@ class SparseMatrix:
         idx = np.ascontiguousarray(idx)
         if ptr.dtype not in (np.int32, np.int64):
             ptr = ptr.astype(np.int64)
+        if idx.dtype == np.int32 and ptr.dtype == np.int64 and int(ptr[-1]) < 2**31 - 8:
+            ptr = ptr.astype(np.int32)  # int32 ids are uploaded as they are (no widened copy of the id array)
         idx = idx.astype(ptr.dtype, copy=False)
         vals = np.ascontiguousarray(vals, dtype=np.float64)
         h = c_p()
@@ -170,6 +185,14 @@ class SparseMatrix:
         k = {"spmv": 0, "residual": 1, "sweep": 2, "spmv_dot": 3, "spmv_add": 4}[mode]
         check(_lib.lib().gsb_bench_rows(self.h, k, reps, ctypes.byref(ms)))
         return float(ms.value)
+
+    def format(self) -> dict:
+        """device storage streamed by the row kernels (gsb_mat_format)"""
+        kind, bs, srt = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        ent, byt = ctypes.c_int64(), ctypes.c_int64()
+        check(_lib.lib().gsb_mat_format(self.h, ctypes.byref(kind), ctypes.byref(bs), ctypes.byref(srt), ctypes.byref(ent), ctypes.byref(byt)))
+        return dict(kind="bsell32" if kind.value == 1 else "csr", block_size=bs.value, sorted=bool(srt.value),
+                    stored_entries=ent.value, bytes_per_pass=byt.value)
 
     def update_values(self, vals):
         vals = np.ascontiguousarray(vals, dtype=np.float64)
@@ -284,6 +307,12 @@ def copy_(dst: Vector, src: Vector) -> Vector:
 
 def consistent_(v: Vector, plan: ExchangePlan) -> Vector:
     check(_lib.lib().gsb_vec_consistent(v.h, plan.h if plan is not None else None))
+    return v
+
+
+def assemble_(v: Vector, plan: ExchangePlan) -> Vector:
+    """assemble!(v) |> wait: ghost contributions added to their owners, ghosts zeroed"""
+    check(_lib.lib().gsb_vec_assemble(v.h, plan.h if plan is not None else None))
     return v
 
 
@@ -418,13 +447,14 @@ def numerical_setup_(ns: NumericalSetup, A, x=None) -> NumericalSetup:
     return ns
 
 
-def solve_(x, ns: NumericalSetup, b):
+def solve_(x, ns: NumericalSetup, b, zero_initial_guess: bool = False):
     """solve!(x,ns,b).  x, b: device `Vector`s, or host numpy arrays of own values (the e2e path:
-    H2D of b and x, solve, D2H of x inside one C call)."""
+    H2D of b and x, solve, D2H of x inside one C call; zero_initial_guess skips the upload of x)."""
     L = _lib.lib()
     if isinstance(x, np.ndarray):
         assert x.dtype == np.float64 and b.dtype == np.float64 and x.flags.c_contiguous and b.flags.c_contiguous
-        check(L.gsb_solve_host(ns.h, _ptr(x), _ptr(b), x.shape[0]))
+        fn = L.gsb_solve_host_zero_guess if zero_initial_guess else L.gsb_solve_host
+        check(fn(ns.h, _ptr(x), _ptr(b), x.shape[0]))
     else:
         check(L.gsb_solve(ns.h, x.h, b.h))
     ns._logs()

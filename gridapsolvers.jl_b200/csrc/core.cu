@@ -6,9 +6,10 @@
 #include <numeric>
 #include <stdexcept>
 
+#include <set>
+
 #include "kernels.cuh"
 #include "ops.h"
-#include "xstage.h"
 
 namespace gsb {
 
@@ -23,12 +24,6 @@ int set_error(gsb_ctx_t ctx, const std::string &msg) {
 }
 const std::string &last_error() { return g_last_error; }
 
-// stream kernel geometry (see kernels.cuh): 256 threads, 16384-entry ring (192 KB), 1024-entry chunks
-constexpr int ST_THREADS = 256;
-constexpr int ST_RING_LOG2 = 14;
-constexpr int ST_CHUNK_LOG2 = 10;
-constexpr int ST_SPAN_MAX = (1 << ST_RING_LOG2) / 2;
-constexpr size_t ST_SMEM = (size_t)(1 << ST_RING_LOG2) * 12 + (size_t)((1 << ST_RING_LOG2) >> ST_CHUNK_LOG2) * 8;
 constexpr int VEC_THREADS = 256;
 constexpr int EW_THREADS = 256;
 constexpr size_t PARTIALS_CAP = (size_t)1 << 20;
@@ -42,8 +37,14 @@ static inline int ew_grid(gsb_ctx_t ctx, int64_t n) {
 static inline void launched(gsb_ctx_t ctx) {
   ctx->launches++;
   cudaError_t e = cudaPeekAtLastError();
-  if (e != cudaSuccess) fail(GSB_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();  // clear the (non-sticky) error so that later launches are not poisoned
+    fail(GSB_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+  }
 }
+
+static std::set<gsb_ctx_t> g_live_ctx;
+bool ctx_alive(gsb_ctx_t ctx) { return g_live_ctx.count(ctx) != 0; }
 
 }  // namespace gsb
 
@@ -51,15 +52,66 @@ using namespace gsb;
 
 // ------------------------------------------------------------------------------------------ ctx
 int gsb_ctx_s::alloc_slots(int n) {
+  // first fit in the ranges returned by destroyed solvers, else bump
+  for (size_t i = 0; i < free_ranges.size(); ++i) {
+    if (free_ranges[i].second >= n) {
+      const int st = free_ranges[i].first;
+      free_ranges[i].first += n;
+      free_ranges[i].second -= n;
+      if (free_ranges[i].second == 0) free_ranges.erase(free_ranges.begin() + (long)i);
+      return st;
+    }
+  }
   if (next_slot + n > (int)scal.n) fail(GSB_ENOMEM, "out of device scalar slots");
-  int s = next_slot;
+  int st = next_slot;
   next_slot += n;
-  return s;
+  return st;
+}
+void gsb_ctx_s::free_slots(int start, int n) {
+  if (n <= 0) return;
+  if (start + n == next_slot) {  // top of the bump region: give it back directly
+    next_slot = start;
+    // absorb free ranges that now touch the top
+    for (bool again = true; again;) {
+      again = false;
+      for (size_t i = 0; i < free_ranges.size(); ++i)
+        if (free_ranges[i].first + free_ranges[i].second == next_slot) {
+          next_slot = free_ranges[i].first;
+          free_ranges.erase(free_ranges.begin() + (long)i);
+          again = true;
+          break;
+        }
+    }
+    return;
+  }
+  // merge with adjacent free ranges
+  for (size_t i = 0; i < free_ranges.size(); ++i) {
+    if (free_ranges[i].first + free_ranges[i].second == start) {
+      free_ranges[i].second += n;
+      for (size_t j = 0; j < free_ranges.size(); ++j)
+        if (j != i && free_ranges[j].first == free_ranges[i].first + free_ranges[i].second) {
+          free_ranges[i].second += free_ranges[j].second;
+          free_ranges.erase(free_ranges.begin() + (long)j);
+          break;
+        }
+      return;
+    }
+    if (start + n == free_ranges[i].first) {
+      free_ranges[i].first = start;
+      free_ranges[i].second += n;
+      return;
+    }
+  }
+  free_ranges.emplace_back(start, n);
 }
 void gsb_ctx_s::read_scalars(int slot, int n, double *out) {
-  GSB_CUDA(cudaMemcpyAsync(h_scal, scal.p + slot, sizeof(double) * n, cudaMemcpyDeviceToHost, stream));
-  GSB_CUDA(cudaStreamSynchronize(stream));
-  for (int i = 0; i < n; ++i) out[i] = h_scal[i];
+  // chunked through the pinned mirror (H_SCAL_READ doubles): a GMRES basis may grow past any fixed size
+  for (int done = 0; done < n; done += H_SCAL_READ) {
+    const int c = std::min(n - done, (int)H_SCAL_READ);
+    GSB_CUDA(cudaMemcpyAsync(h_scal, scal.p + slot + done, sizeof(double) * c, cudaMemcpyDeviceToHost, stream));
+    GSB_CUDA(cudaStreamSynchronize(stream));
+    for (int i = 0; i < c; ++i) out[done + i] = h_scal[i];
+  }
 }
 double gsb_ctx_s::read_scalar(int slot) {
   double v;
@@ -165,8 +217,71 @@ void inv_diag(gsb_mat_t A, double *invd) {
   gsb_ctx_t ctx = A->ctx;
   if (A->n_rows == 0) return;
   int grid = (int)((A->n_rows + 255) / 256);
-  inv_diag_kernel<<<grid, 256, 0, ctx->stream>>>(A->n_rows, A->rowptr.p, A->col.p, A->val.p, invd);
+  inv_diag_kernel<<<grid, 256, 0, ctx->stream>>>(A->n_rows, A->diag.p, invd);
   launched(ctx);
+}
+
+void csr_diag(gsb_mat_t A, const double *dval) {
+  gsb_ctx_t ctx = A->ctx;
+  A->diag_pos.alloc((size_t)std::max<int64_t>(1, A->n_rows));
+  if (A->n_rows == 0) return;
+  csr_diag_kernel<<<(unsigned)((A->n_rows + 255) / 256), 256, 0, ctx->stream>>>(A->n_rows, A->rowptr.p, A->col.p, dval, A->diag.p,
+                                                                              A->diag_pos.p);
+  launched(ctx);
+}
+
+void refresh_diag(gsb_mat_t A, const double *dval) {
+  gsb_ctx_t ctx = A->ctx;
+  if (A->n_rows == 0) return;
+  refresh_diag_kernel<<<(unsigned)((A->n_rows + 255) / 256), 256, 0, ctx->stream>>>(A->n_rows, A->diag_pos.p, dval, A->diag.p);
+  launched(ctx);
+}
+
+// CSR (device) -> block-SELL (device); values_only refreshes the values of an existing layout.  The CSR
+// column ids are only needed for the full build.
+void sell_fill(gsb_mat_t A, bool values_only, const double *dval) {
+  gsb_ctx_t ctx = A->ctx;
+  const int64_t npos = A->n_slices * 32;
+  if (npos == 0) return;
+  const unsigned grid = (unsigned)((npos + 255) / 256);
+  const int *perm = A->sorted ? A->sell_perm.p : nullptr;
+  const int vo = values_only ? 1 : 0;
+  switch (A->bs) {
+    case 1: sell_fill_kernel<1><<<grid, 256, 0, ctx->stream>>>(npos, A->n_brows, perm, A->sell_off.p, A->rowptr.p, A->col.p, dval, A->sell_bcol.p, A->sell_val.p, vo); break;
+    case 2: sell_fill_kernel<2><<<grid, 256, 0, ctx->stream>>>(npos, A->n_brows, perm, A->sell_off.p, A->rowptr.p, A->col.p, dval, A->sell_bcol.p, A->sell_val.p, vo); break;
+    case 3: sell_fill_kernel<3><<<grid, 256, 0, ctx->stream>>>(npos, A->n_brows, perm, A->sell_off.p, A->rowptr.p, A->col.p, dval, A->sell_bcol.p, A->sell_val.p, vo); break;
+    default: fail(GSB_EINVAL, "block-SELL: unsupported block size");
+  }
+  launched(ctx);
+}
+
+// modified Gram-Schmidt step: w -= scal[slot_prev] * vprev (skipped when vprev == nullptr) ; scal[slot] = w.v (v == nullptr: w.w)
+void mgs_step(gsb_vec_s &w, const gsb_vec_s *vprev, int slot_prev, const gsb_vec_s *v, int slot) {
+  gsb_ctx_t ctx = w.ctx;
+  GSB_CHECK((!vprev || vprev->n_own == w.n_own) && (!v || v->n_own == w.n_own), "mgs: own sizes differ");
+  int grid = ew_grid(ctx, std::max<int64_t>(w.n_own, 1));
+  mgs_step_kernel<EW_THREADS><<<grid, EW_THREADS, 0, ctx->stream>>>(w.n_own, w.d, vprev ? vprev->d : nullptr, slot_prev,
+                                                                    v ? v->d : nullptr, ctx->reduce_out(slot));
+  launched(ctx);
+  ctx->allreduce_slot(slot);
+}
+
+// x += sum_i g[i] * z[i], vector after vector per element, MAXPY_MAX vectors per launch
+void multi_axpy(gsb_vec_s &x, const std::vector<const gsb_vec_s *> &z, const double *g) {
+  gsb_ctx_t ctx = x.ctx;
+  if (x.n_own == 0) return;
+  for (size_t done = 0; done < z.size(); done += MAXPY_MAX) {
+    MultiAxpyArgs a{};
+    a.x = x.d; a.n = x.n_own;
+    a.cnt = (int)std::min<size_t>(MAXPY_MAX, z.size() - done);
+    for (int q = 0; q < a.cnt; ++q) {
+      GSB_CHECK(z[done + q]->n_own == x.n_own, "multi_axpy: own sizes differ");
+      a.z[q] = z[done + q]->d;
+      a.g[q] = g[done + q];
+    }
+    multi_axpy_kernel<EW_THREADS><<<ew_grid(ctx, x.n_own), EW_THREADS, 0, ctx->stream>>>(a);
+    launched(ctx);
+  }
 }
 
 // ---------------------------------------------------------------- halo exchange (consistent!)
@@ -239,75 +354,108 @@ void consistent_end(gsb_vec_s &v, gsb_plan_t plan) {
   GSB_CUDA(cudaStreamWaitEvent(v.ctx->stream, v.ctx->ev_b, 0));
 }
 
+// assemble!(v) (PartitionedArrays: ghost contributions are sent to the owners and added there, neighbour
+// after neighbour in the order of the assembly cache, then the ghost entries are zeroed).  The reverse of
+// consistent!: what the plan receives is sent, what it sends is received.  Call sites in the reference:
+// LinearSolvers/SchwarzLinearSolvers.jl:44-49, MultilevelTools/GridTransferOperators.jl:425,544.
+// Not on the Krylov/GMG hot path of this library (restrictions are stored with owned rows), so it always
+// takes the NCCL send/recv route.
+void assemble(gsb_vec_s &v, gsb_plan_t plan) {
+  if (!plan_active(v, plan)) {
+    // single part: no contributions to move, but the contract still zeroes the ghost tail
+    if (v.n_ghost) GSB_CUDA(cudaMemsetAsync(v.d + v.n_own, 0, sizeof(double) * v.n_ghost, v.ctx->stream));
+    return;
+  }
+  gsb_ctx_t ctx = v.ctx;
+  cudaStream_t st = ctx->stream;
+  const int64_t nsnd = plan->snd_ptrs.back(), nrcv = plan->rcv_ptrs.back();
+  if (nrcv) {  // ghost values -> packed buffer (the plan's receive side is the send side here)
+    int grid = (int)std::min<int64_t>((nrcv + 255) / 256, 1024);
+    pack_kernel<<<grid, 256, 0, st>>>(nrcv, plan->rcv_ids.p, v.d, plan->rcv_buf.p);
+    launched(ctx);
+  }
+  GSB_NCCL(ncclGroupStart());
+  for (size_t k = 0; k < plan->nbr_snd.size(); ++k) {
+    const int64_t off = plan->snd_ptrs[k], cnt = plan->snd_ptrs[k + 1] - off;
+    if (cnt) GSB_NCCL(ncclRecv(plan->snd_buf.p + off, cnt, ncclDouble, plan->nbr_snd[k], ctx->comm, st));
+  }
+  for (size_t k = 0; k < plan->nbr_rcv.size(); ++k) {
+    const int64_t off = plan->rcv_ptrs[k], cnt = plan->rcv_ptrs[k + 1] - off;
+    if (cnt) GSB_NCCL(ncclSend(plan->rcv_buf.p + off, cnt, ncclDouble, plan->nbr_rcv[k], ctx->comm, st));
+  }
+  GSB_NCCL(ncclGroupEnd());
+  // owners add the contributions neighbour after neighbour (an own entry may be a ghost of several parts:
+  // the order of the additions is the order of the neighbours, as in the reference's sequential loop)
+  for (size_t k = 0; k < plan->nbr_snd.size(); ++k) {
+    const int64_t off = plan->snd_ptrs[k], cnt = plan->snd_ptrs[k + 1] - off;
+    if (!cnt) continue;
+    int grid = (int)std::min<int64_t>((cnt + 255) / 256, 1024);
+    add_at_kernel<<<grid, 256, 0, st>>>(cnt, plan->snd_ids.p + off, plan->snd_buf.p + off, v.d);
+    launched(ctx);
+  }
+  if (nsnd == 0 && nrcv == 0) return;
+  if (v.n_ghost) GSB_CUDA(cudaMemsetAsync(v.d + v.n_own, 0, sizeof(double) * v.n_ghost, st));
+}
+
 // ---------------------------------------------------------------- row kernels
-template <int G, int MODE>
-static void launch_stream(gsb_mat_t A, RowArgs &a) {
-  gsb_ctx_t ctx = A->ctx;
-  auto kern = csr_stream_kernel<G, MODE, ST_THREADS, ST_RING_LOG2, ST_CHUNK_LOG2>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
-    attr_set = true;
-  }
-  StreamArgs m{A->rowptr.p, A->col.p, A->val.p, A->cta_rows.p, A->nnz_padded};
-  kern<<<A->n_ctas, ST_THREADS, ST_SMEM, ctx->stream>>>(m, a);
-  launched(ctx);
-}
-
-// warp-specialised variant: NW consumer warps + 1 producer warp, U gathers in flight per lane
-constexpr int WS_NW = 8;
-constexpr int WS_U = 9;
-template <int G, int MODE>
-static void launch_stream_ws(gsb_mat_t A, RowArgs &a) {
-  gsb_ctx_t ctx = A->ctx;
-  auto kern = csr_stream_ws_kernel<G, MODE, WS_NW, ST_RING_LOG2, ST_CHUNK_LOG2, WS_U>;
-  constexpr size_t smem = (size_t)(1 << ST_RING_LOG2) * 12 + (size_t)((1 << ST_RING_LOG2) >> ST_CHUNK_LOG2) * 16;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
-  StreamArgs m{A->rowptr.p, A->col.p, A->val.p, A->cta_rows.p, A->nnz_padded};
-  kern<<<A->n_ctas, (WS_NW + 1) * 32, smem, ctx->stream>>>(m, a);
-  launched(ctx);
-}
-
+// block-SELL launch: one warp per slice.  Unroll depth / register budget per block size (9 scalar entries,
+// 4 2x2 blocks or 2 3x3 blocks in flight per lane; profiles/sell_variants_r0*.json): the loads of one
+// unrolled step must all be issued before the first dependent DMUL, which needs ~62 (BS=1) .. ~96 (BS=3)
+// registers -- a smaller budget serialises them and loses 30 %.
 constexpr int SELL_THREADS = 256;
-constexpr int SELL_U = 9;
+template <int MODE, int BS, bool PERM>
+static void launch_sell_inst(gsb_ctx_t ctx, const SellArgs &m, const RowArgs &a, unsigned grid, int variant) {
+#define GSB_SELL(U_, MINB_) sell_kernel<MODE, BS, PERM, SELL_THREADS, U_, MINB_><<<grid, SELL_THREADS, 0, ctx->stream>>>(m, a)
+  if constexpr (BS == 1) {
+    switch (variant) {
+      case 1: GSB_SELL(9, 3); break;
+      case 2: GSB_SELL(14, 2); break;
+      default:
+        // the fused-dot mode prefers the 70-register schedule (its block reduction keeps fewer CTAs busy at the tail)
+        if (MODE == ROW_SPMV_DOT) GSB_SELL(9, 1);
+        else GSB_SELL(9, 4);
+        break;
+    }
+  } else if constexpr (BS == 2) {
+    switch (variant) {
+      case 1: GSB_SELL(3, 3); break;
+      case 2: GSB_SELL(6, 2); break;
+      default: GSB_SELL(4, 3); break;
+    }
+  } else {
+    switch (variant) {
+      case 1: GSB_SELL(1, 4); break;
+      case 2: GSB_SELL(3, 2); break;
+      default: GSB_SELL(2, 3); break;
+    }
+  }
+#undef GSB_SELL
+}
+
 template <int MODE>
 static void launch_sell_list(gsb_mat_t A, RowArgs &a, const int *list, int64_t n_list) {
   gsb_ctx_t ctx = A->ctx;
   if (n_list == 0 && MODE != ROW_SPMV_DOT) return;
   const int64_t grid = std::max<int64_t>(1, (n_list * 32 + SELL_THREADS - 1) / SELL_THREADS);
   if (MODE == ROW_SPMV_DOT) GSB_CHECK((size_t)grid <= PARTIALS_CAP, "matrix too large for the fused dot");
-  SellArgs m{list, n_list, A->rowptr.p, A->sell_off.p, A->sell_col.p, A->sell_val.p, A->n_rows};
+  SellArgs m{list, n_list, A->sell_perm.p, A->sell_blen.p, A->sell_off.p, A->sell_bcol.p, A->sell_val.p, A->n_brows};
   const int variant = std::stoi(ctx->opt("sell_variant", "0"));
-#define GSB_SELL(U_, MINB_, STYLE_) \
-  csr_sell_kernel<MODE, SELL_THREADS, U_, MINB_, STYLE_><<<(unsigned)grid, SELL_THREADS, 0, ctx->stream>>>(m, a)
-  switch (variant) {
-    case 1: GSB_SELL(9, 4, 0); break;
-    case 2: GSB_SELL(9, 3, 1); break;
-    case 3: GSB_SELL(27, 1, 1); break;
-    case 4: GSB_SELL(14, 2, 1); break;
-    case 5: GSB_SELL(9, 8, 1); break;
-    case 6: GSB_SELL(27, 2, 1); break;
-    case 7: GSB_SELL(9, 4, 1); break;
-    case 8: GSB_SELL(SELL_U, 1, 0); break;
-    default:
-      // 9 independent loads in flight per lane need ~62 registers; a 32-register build serialises
-      // them and loses 30 % (profiles/sell_variants_r01.json).  The fused-dot mode prefers the
-      // 70-register schedule (its block reduction keeps fewer CTAs busy at the tail).
-      if (MODE == ROW_SPMV_DOT) GSB_SELL(SELL_U, 1, 0);
-      else GSB_SELL(SELL_U, 4, 1);
-      break;
+  const unsigned g = (unsigned)grid;
+  switch (A->bs * 2 + (A->sorted ? 1 : 0)) {
+    case 2: launch_sell_inst<MODE, 1, false>(ctx, m, a, g, variant); break;
+    case 3: launch_sell_inst<MODE, 1, true>(ctx, m, a, g, variant); break;
+    case 4: launch_sell_inst<MODE, 2, false>(ctx, m, a, g, variant); break;
+    case 5: launch_sell_inst<MODE, 2, true>(ctx, m, a, g, variant); break;
+    case 6: launch_sell_inst<MODE, 3, false>(ctx, m, a, g, variant); break;
+    case 7: launch_sell_inst<MODE, 3, true>(ctx, m, a, g, variant); break;
+    default: fail(GSB_EINVAL, "block-SELL: unsupported block size");
   }
-#undef GSB_SELL
   launched(ctx);
 }
 
 template <int MODE>
 static void launch_sell(gsb_mat_t A, RowArgs &a) {
-  launch_sell_list<MODE>(A, a, nullptr, (A->n_rows + 31) / 32);
+  launch_sell_list<MODE>(A, a, nullptr, A->n_slices);
 }
 
 // halo overlap: the interior slices (no ghost column in any of their rows) run while the exchange is
@@ -323,17 +471,22 @@ static void launch_sell_split(gsb_mat_t A, RowArgs &a, gsb_vec_s &xvec) {
   launch_sell_list<MODE>(A, a, A->bnd_slices.p, A->n_bnd_slices);
 }
 
+static bool use_sell(gsb_mat_t A) {
+  const std::string pref = A->ctx->opt("spmv", "auto");
+  return A->sell_ok && (pref != "vector" || !A->csr_kept);
+}
+
 static bool use_split(gsb_mat_t A) {
   gsb_ctx_t ctx = A->ctx;
   const bool force = ctx->opt("force_split", "0") == "1";  // diagnostics: split kernels on one rank
-  return A->split_ok && A->sell_ok && ((ctx->nranks > 1 && A->plan) || force) && ctx->opt("overlap", "0") == "1" &&
-         ctx->opt("spmv", "auto") != "vector" && ctx->opt("spmv", "auto") != "stream" &&
+  return A->split_ok && use_sell(A) && ((ctx->nranks > 1 && A->plan) || force) && ctx->opt("overlap", "0") == "1" &&
          A->n_rows >= (int64_t)std::stoll(ctx->opt("overlap_min_rows", "100000"));
 }
 
 template <int G, int MODE>
 static void launch_vector(gsb_mat_t A, RowArgs &a) {
   gsb_ctx_t ctx = A->ctx;
+  GSB_CHECK(A->csr_kept, "internal: CSR fallback kernel on a matrix whose CSR arrays were released");
   const int64_t threads = A->n_rows * G;
   const int64_t grid = std::max<int64_t>(1, (threads + VEC_THREADS - 1) / VEC_THREADS);
   if (MODE == ROW_SPMV_DOT) GSB_CHECK((size_t)grid <= PARTIALS_CAP, "matrix too large for the vector kernel's fused dot");
@@ -342,19 +495,15 @@ static void launch_vector(gsb_mat_t A, RowArgs &a) {
   launched(ctx);
 }
 
+// kernel-kind codes reported by the profiler: 0 csr_vector, 2 block-SELL (+ 10*bs, +100 when sorted)
 template <int MODE>
 static void launch_rows(gsb_mat_t A, RowArgs &a) {
   gsb_ctx_t ctx = A->ctx;
   if (A->n_rows == 0 && MODE != ROW_SPMV_DOT) return;
-  const std::string pref = ctx->opt("spmv", "auto");
-  const int span_rows = ST_SPAN_MAX / std::max(1, A->max_row_nnz);
-  bool stream = A->stream_ok && span_rows >= 1;
-  if (pref == "vector") stream = false;
-  else if (pref == "auto") stream = stream && A->n_rows >= (int64_t)std::stoll(ctx->opt("stream_min_rows", "65536"));
-  if (A->n_rows == 0) stream = false;
+  const bool sell = use_sell(A);
   gsb_ctx_s::ProfRec rec{};
   if (ctx->profiling) {
-    rec.mode = MODE; rec.stream = stream ? 1 : 0; rec.nrows = A->n_rows; rec.nnz = A->nnz;
+    rec.mode = MODE; rec.stream = sell ? 2 + 10 * A->bs + (A->sorted ? 100 : 0) : 0; rec.nrows = A->n_rows; rec.nnz = A->nnz;
     GSB_CUDA(cudaEventCreate(&rec.e0));
     GSB_CUDA(cudaEventCreate(&rec.e1));
     GSB_CUDA(cudaEventRecord(rec.e0, ctx->stream));
@@ -363,42 +512,14 @@ static void launch_rows(gsb_mat_t A, RowArgs &a) {
     gsb_ctx_t c; gsb_ctx_s::ProfRec *r;
     ~ProfEnd() { if (c->profiling) { cudaEventRecord(r->e1, c->stream); c->prof.push_back(*r); } }
   } prof_end{ctx, &rec};
-  const bool sell = A->sell_ok && (pref == "sell" || (pref == "auto" && A->n_rows >= (int64_t)std::stoll(ctx->opt("sell_min_rows", "1"))));
-  rec.stream = sell ? 2 : rec.stream;
-  if (sell && A->xs_ok && ctx->opt("xstage", "0") == "1") {
-    XStageArgs m{A->rowptr.p, A->sell_off.p, A->xs_lcol.p, A->sell_val.p, A->xs_chunk_seg_ptr.p,
-                 A->xs_seg_start.p, A->xs_seg_len.p, A->xs_seg_off.p, A->n_rows};
-    const int64_t grid = (A->n_rows + 255) / 256;
-    if (MODE == ROW_SPMV_DOT) GSB_CHECK((size_t)grid <= PARTIALS_CAP, "matrix too large for the fused dot");
-    csr_sell_xs_kernel<MODE, 256, SELL_U><<<(unsigned)grid, 256, sizeof(double) * (size_t)A->xs_max_window, ctx->stream>>>(m, a);
-    launched(ctx);
-    rec.stream = 3;
-    return;
-  }
   if (sell) {
     launch_sell<MODE>(A, a);
     return;
   }
-  // the warp-specialised kernel needs a warp step (32/G rows) to fit half the ring
-  const bool ws_ok = (int64_t)A->max_row_nnz * (32 / A->G) <= ST_SPAN_MAX;
-  if (stream && ws_ok && ctx->opt("stream_kernel", "ws") == "ws") {
-    switch (A->G) {
-      case 1: launch_stream_ws<1, MODE>(A, a); break;
-      case 4: launch_stream_ws<4, MODE>(A, a); break;
-      default: launch_stream_ws<16, MODE>(A, a); break;
-    }
-  } else if (stream) {
-    switch (A->G) {
-      case 1: launch_stream<1, MODE>(A, a); break;
-      case 4: launch_stream<4, MODE>(A, a); break;
-      default: launch_stream<16, MODE>(A, a); break;
-    }
-  } else {
-    switch (A->G) {
-      case 1: launch_vector<1, MODE>(A, a); break;
-      case 4: launch_vector<4, MODE>(A, a); break;
-      default: launch_vector<16, MODE>(A, a); break;
-    }
+  switch (A->G) {
+    case 1: launch_vector<1, MODE>(A, a); break;
+    case 4: launch_vector<4, MODE>(A, a); break;
+    default: launch_vector<16, MODE>(A, a); break;
   }
 }
 
@@ -474,49 +595,6 @@ void sweep(gsb_mat_t A, gsb_vec_s &dx_in, gsb_vec_s &r, const double *invd, doub
   else launch_rows<ROW_SWEEP>(A, a);
 }
 
-constexpr int PIPE_THREADS = 256;
-bool sweeps_pipelined(gsb_mat_t A, const double *invd, double omega, int niter, gsb_vec_s &r, gsb_vec_s &x,
-                      gsb_vec_s &dxa, gsb_vec_s &dxb) {
-  gsb_ctx_t ctx = A->ctx;
-  const int smax = std::stoi(ctx->opt("pipe_stages", "1"));  // opt-in: see DESIGN.md section 5 (no net gain measured)
-  if (smax < 2 || niter < 2 || !A->sell_ok || A->nb > 0 || A->n_ghost_cols > 0 || A->n_rows != A->n_own_cols) return false;
-  const int grid = ctx->num_sms * std::min(4, std::max(1, std::stoi(ctx->opt("pipe_ctas_per_sm", "4"))));
-  const int nchunks = (int)((A->n_rows + PIPE_THREADS - 1) / PIPE_THREADS);
-  if (nchunks < (int)std::stoll(ctx->opt("pipe_min_chunks", std::to_string(4 * grid)))) return false;
-  const int reach = (int)(A->bw_rows / PIPE_THREADS) + 1;
-  if (A->pipe_ctr.n == 0) {
-    A->pipe_ctr.alloc(2);
-    A->pipe_prefix.alloc(32);
-    A->pipe_done.alloc((size_t)32 * (size_t)nchunks);
-    GSB_CUDA(cudaMemsetAsync(A->pipe_ctr.p, 0, 2 * sizeof(unsigned int), ctx->stream));
-    GSB_CUDA(cudaMemsetAsync(A->pipe_prefix.p, 0, 32 * sizeof(int), ctx->stream));
-    GSB_CUDA(cudaMemsetAsync(A->pipe_done.p, 0, sizeof(int) * 32 * (size_t)nchunks, ctx->stream));
-  }
-  int k0 = 1;
-  while (k0 <= niter) {
-    const int S = std::min(std::min(smax, 32), niter - k0 + 1);
-    PipeArgs p{};
-    p.m = SellArgs{nullptr, (A->n_rows + 31) / 32, A->rowptr.p, A->sell_off.p, A->sell_col.p, A->sell_val.p, A->n_rows};
-    p.r = r.d; p.x = x.d; p.invd = invd; p.dxbuf[0] = dxa.d; p.dxbuf[1] = dxb.d; p.omega = omega;
-    p.k0 = k0; p.S = S; p.niter = niter; p.nchunks = nchunks; p.reach = reach;
-    p.lag = reach + (grid + S - 1) / S + std::stoi(ctx->opt("pipe_lag_margin", "64"));
-    p.ticket = A->pipe_ctr.p; p.exited = A->pipe_ctr.p + 1; p.prefix = A->pipe_prefix.p; p.done = A->pipe_done.p;
-    p.epoch = ++A->pipe_epoch;
-    p.l2_hints = ctx->opt("pipe_l2_hints", "1") == "1";
-    gsb_ctx_s::ProfRec rec{};
-    if (ctx->profiling) {
-      rec.mode = 5; rec.stream = 100 + S; rec.nrows = A->n_rows; rec.nnz = A->nnz;
-      GSB_CUDA(cudaEventCreate(&rec.e0)); GSB_CUDA(cudaEventCreate(&rec.e1));
-      GSB_CUDA(cudaEventRecord(rec.e0, ctx->stream));
-    }
-    sell_pipe_kernel<PIPE_THREADS, SELL_U><<<grid, PIPE_THREADS, 0, ctx->stream>>>(p);
-    launched(ctx);
-    if (ctx->profiling) { GSB_CUDA(cudaEventRecord(rec.e1, ctx->stream)); ctx->prof.push_back(rec); }
-    k0 += S;
-  }
-  return true;
-}
-
 void spmv_dot(gsb_mat_t A, gsb_vec_s &x, gsb_vec_s &y, const gsb_vec_s &dotv, int slot) {
   gsb_ctx_t ctx = A->ctx;
   if (A->nb > 0) {
@@ -549,6 +627,7 @@ void spmv_add(gsb_mat_t A, gsb_vec_s &x, gsb_vec_s &y, gsb_vec_s &xacc) {
 void dense_inverse_rows(gsb_mat_t A, DevBuf<double> &inv_rows, int64_t &n_global, int64_t &row_off) {
   gsb_ctx_t ctx = A->ctx;
   GSB_CHECK(A->nb == 0, "dense LU: block matrices not supported");
+  GSB_CHECK(A->csr_kept, "dense LU: matrix too large for the dense coarse solver (CSR arrays released)");
   // global numbering: own rows of rank p are [off_p, off_p + n_own_p)  (PartitionedArrays own-first gids)
   std::vector<int64_t> counts((size_t)ctx->nranks, 0);
   counts[(size_t)ctx->rank] = A->n_rows;
@@ -609,17 +688,25 @@ void dense_inverse_rows(gsb_mat_t A, DevBuf<double> &inv_rows, int64_t &n_global
   }
   gj_set_identity_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, M.p);
   launched(ctx);
-  DevBuf<int> piv(1);
-  DevBuf<double> pivval(1), prow((size_t)2 * n), fcol((size_t)n);
-  const unsigned gcols = (unsigned)((2 * n + 255) / 256);
-  for (int64_t k = 0; k < n; ++k) {
-    gj_pivot_kernel<<<1, 256, 0, ctx->stream>>>(n, k, M.p, piv.p, pivval.p);
-    gj_fcol_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, k, M.p, piv.p, fcol.p);
-    gj_swap_scale_kernel<<<gcols, 256, 0, ctx->stream>>>(n, k, M.p, piv.p, pivval.p, prow.p);
-    gj_eliminate_kernel<<<dim3(gcols, (unsigned)n), 256, 0, ctx->stream>>>(n, k, M.p, prow.p, fcol.p);
-    ctx->launches += 4;
+  if (n > 0) {
+    // the whole elimination is ONE cooperative launch (grid barriers between the phases of a column)
+    constexpr int GJ_THREADS = 256;
+    int per_sm = 0;
+    GSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gj_inverse_kernel<GJ_THREADS>, GJ_THREADS, 0));
+    GSB_CHECK(per_sm >= 1, "dense coarse solver: cooperative kernel does not fit on an SM");
+    // enough CTAs to cover the rows, never more than are co-resident
+    int grid = (int)std::min<int64_t>((int64_t)ctx->num_sms * std::min(per_sm, 4), std::max<int64_t>(1, n));
+    DevBuf<double> prow((size_t)2 * n), fcol((size_t)n), cabs((size_t)grid), cval((size_t)grid);
+    DevBuf<int> cidx((size_t)grid);
+    DevBuf<unsigned int> bar(1);
+    GSB_CUDA(cudaMemsetAsync(bar.p, 0, sizeof(unsigned int), ctx->stream));
+    GJArgs ga{n, M.p, prow.p, fcol.p, cabs.p, cval.p, cidx.p, bar.p};
+    void *args[] = {&ga};
+    GSB_CUDA(cudaLaunchCooperativeKernel((void *)gj_inverse_kernel<GJ_THREADS>, dim3((unsigned)grid), dim3(GJ_THREADS), args, 0,
+                                         ctx->stream));
+    launched(ctx);
+    GSB_CUDA(cudaStreamSynchronize(ctx->stream));  // scratch buffers go out of scope
   }
-  launched(ctx);
   inv_rows.alloc((size_t)std::max<int64_t>(1, A->n_rows) * n);
   if (A->n_rows) {
     gj_extract_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)A->n_rows), 256, 0, ctx->stream>>>(n, row_off, A->n_rows,
@@ -649,32 +736,11 @@ void dense_apply(gsb_ctx_t ctx, const DevBuf<double> &inv_rows, int64_t n_global
 }  // namespace gsb
 
 // ------------------------------------------------------------------------------------------ C ABI
-#define GSB_NULLCHK(h)                                         \
-  if (!(h)) {                                                 \
-    gsb::set_error(nullptr, "NULL handle passed to libgsb200"); \
-    return GSB_EINVAL;                                        \
-  }
-#define API_BEGIN try {
-#define API_END(ctx)                               \
-  }                                                \
-  catch (const gsb::Error &e) {                    \
-    gsb::set_error((ctx), e.msg);                  \
-    return e.code;                                 \
-  }                                                \
-  catch (const std::exception &e) {                \
-    gsb::set_error((ctx), e.what());               \
-    return GSB_EINVAL;                             \
-  }                                                \
-  return GSB_OK;
-
-namespace gsb {
-int set_error(gsb_ctx_t ctx, const std::string &msg);
-const std::string &last_error();
-}  // namespace gsb
+#include "api_macros.h"
 
 extern "C" {
 
-int gsb_version(void) { return 100; }
+int gsb_version(void) { return 200; }
 
 const char *gsb_last_error(gsb_ctx_t ctx) {
   (void)ctx;
@@ -731,7 +797,7 @@ int gsb_init(int device, int nranks, int rank, const void *nccl_id, gsb_ctx_t *o
   ctx->partials.alloc(PARTIALS_CAP);
   ctx->ticket.alloc(4);
   GSB_CUDA(cudaMemset(ctx->ticket.p, 0, sizeof(unsigned int) * 4));
-  GSB_CUDA(cudaMallocHost(&ctx->h_scal, sizeof(double) * 256));
+  GSB_CUDA(cudaMallocHost(&ctx->h_scal, sizeof(double) * (gsb_ctx_s::H_SCAL_READ + 8)));
   if (nranks > 1) {
     GSB_CHECK(nccl_id != nullptr, "gsb_init: nccl id required for nranks > 1");
     ncclUniqueId id;
@@ -739,12 +805,14 @@ int gsb_init(int device, int nranks, int rank, const void *nccl_id, gsb_ctx_t *o
     GSB_NCCL(ncclCommInitRank(&ctx->comm, nranks, id, rank));
   }
   *out = ctx.release();
+  gsb::g_live_ctx.insert(*out);
   API_END(nullptr)
 }
 
 int gsb_finalize(gsb_ctx_t ctx) {
   API_BEGIN
   if (!ctx) return GSB_OK;
+  gsb::g_live_ctx.erase(ctx);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->comm) ncclCommDestroy(ctx->comm);
   if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
@@ -819,41 +887,6 @@ int gsb_profile_stop(gsb_ctx_t ctx, int cap, int *n_out, int *mode, int *stream,
   ctx->prof.clear();
   *n_out = n;
   API_END(ctx)
-}
-
-// diagnostics (pure host, no device needed): plan of the staged-x-window kernel for a CSR matrix.
-// out[0] = ok, out[1] = chunks, out[2] = segments, out[3] = max window, out[4] = total window (doubles);
-// lcol_check (optional, nnz entries, CSR order) receives seg_start + (lcol - seg_off) of every entry, i.e. the
-// column the kernel would gather -- it must equal `col`.
-int gsb_diag_xstage_plan(int64_t n_rows, const int *rowptr, const int *col, int chunk_rows, int gap, int cap,
-                         int64_t *out, int *lcol_check) {
-  API_BEGIN
-  GSB_CHECK(rowptr && col && out && chunk_rows >= 32 && chunk_rows % 32 == 0, "xstage plan: bad arguments");
-  const int64_t nsl = (n_rows + 31) / 32;
-  std::vector<int> soff((size_t)nsl + 1, 0);
-  for (int64_t sl = 0; sl < nsl; ++sl) {
-    int w = 0;
-    for (int64_t i = sl * 32; i < std::min<int64_t>(n_rows, sl * 32 + 32); ++i) w = std::max(w, rowptr[i + 1] - rowptr[i]);
-    soff[(size_t)sl + 1] = soff[(size_t)sl] + w;
-  }
-  XStagePlan xp = build_xstage(n_rows, rowptr, col, soff.data(), chunk_rows, gap, cap);
-  out[0] = xp.ok; out[1] = (int64_t)xp.chunk_seg_ptr.size() - 1; out[2] = (int64_t)xp.seg_start.size();
-  out[3] = xp.max_window; out[4] = xp.total_window;
-  if (xp.ok && lcol_check) {
-    for (int64_t i = 0; i < n_rows; ++i) {
-      const int64_t c = i / chunk_rows;
-      const size_t base = ((size_t)soff[(size_t)(i >> 5)] << 5) + (size_t)(i & 31);
-      for (int e = rowptr[i], k = 0; e < rowptr[i + 1]; ++e, ++k) {
-        const int lc = xp.lcol[base + (size_t)k * 32];
-        int found = -1;
-        for (int sg = xp.chunk_seg_ptr[(size_t)c]; sg < xp.chunk_seg_ptr[(size_t)c + 1]; ++sg)
-          if (lc >= xp.seg_off[(size_t)sg] && lc < xp.seg_off[(size_t)sg] + xp.seg_len[(size_t)sg])
-            found = xp.seg_start[(size_t)sg] + (lc - xp.seg_off[(size_t)sg]);
-        lcol_check[e] = found;
-      }
-    }
-  }
-  API_END(nullptr)
 }
 
 // diagnostics: time `reps` back-to-back launches of one row-kernel mode on scratch vectors
@@ -1054,267 +1087,6 @@ int gsb_plan_destroy(gsb_plan_t plan) {
   return GSB_OK;
 }
 
-// ---------------------------------------------------------------- matrix
-static int64_t rd_idx(const void *p, int bytes, int64_t i) {
-  return bytes == 8 ? ((const int64_t *)p)[i] : (int64_t)((const int32_t *)p)[i];
-}
-
-static void finish_matrix(gsb_mat_s *A, const std::vector<int> &rowptr, const std::vector<int> &col,
-                          const std::vector<double> &val) {
-  gsb_ctx_t ctx = A->ctx;
-  A->nnz = (int64_t)col.size();
-  A->nnz_padded = (A->nnz + 3) & ~(int64_t)3;
-  if (A->nnz_padded == 0) A->nnz_padded = 4;
-  A->rowptr.alloc(rowptr.size());
-  A->col.alloc((size_t)A->nnz_padded);
-  A->val.alloc((size_t)A->nnz_padded);
-  GSB_CUDA(cudaMemset(A->col.p, 0, sizeof(int) * A->nnz_padded));
-  GSB_CUDA(cudaMemset(A->val.p, 0, sizeof(double) * A->nnz_padded));
-  GSB_CUDA(cudaMemcpy(A->rowptr.p, rowptr.data(), sizeof(int) * rowptr.size(), cudaMemcpyHostToDevice));
-  if (A->nnz) {
-    GSB_CUDA(cudaMemcpy(A->col.p, col.data(), sizeof(int) * col.size(), cudaMemcpyHostToDevice));
-    GSB_CUDA(cudaMemcpy(A->val.p, val.data(), sizeof(double) * val.size(), cudaMemcpyHostToDevice));
-  }
-  int mx = 0;
-  for (int64_t i = 0; i < A->n_rows; ++i) mx = std::max(mx, rowptr[(size_t)i + 1] - rowptr[(size_t)i]);
-  A->max_row_nnz = mx;
-  {
-    int64_t bw = 0;
-    for (int64_t i = 0; i < A->n_rows; ++i)
-      for (int e = rowptr[(size_t)i]; e < rowptr[(size_t)i + 1]; ++e)
-        if (col[(size_t)e] < A->n_own_cols) bw = std::max<int64_t>(bw, std::llabs((int64_t)col[(size_t)e] - i));
-    A->bw_rows = bw;
-  }
-  const double avg = A->n_rows ? (double)A->nnz / (double)A->n_rows : 0.0;
-  A->G = avg <= 48.0 ? 1 : (avg <= 160.0 ? 4 : 16);
-  A->stream_ok = mx <= ST_SPAN_MAX && A->n_rows > 0;
-  // SELL-32 mirror for one-lane-per-row matrices with little padding
-  A->sell_ok = false;
-  if (A->G == 1 && A->n_rows > 0 && ctx->opt("sell", "1") == "1") {
-    const int64_t nsl = (A->n_rows + 31) / 32;
-    std::vector<int> soff((size_t)nsl + 1, 0);
-    int64_t tot = 0;
-    for (int64_t sl = 0; sl < nsl; ++sl) {
-      int w = 0;
-      for (int64_t i = sl * 32; i < std::min<int64_t>(A->n_rows, sl * 32 + 32); ++i)
-        w = std::max(w, rowptr[(size_t)i + 1] - rowptr[(size_t)i]);
-      tot += w;
-      soff[(size_t)sl + 1] = (int)tot;
-    }
-    const int64_t entries = tot * 32;
-    // padding budget: 25 %; very short rows (prolongations: 1/2/4/8 entries) may pad up to 3x -- a padded
-    // coalesced slice still beats the row-pointer-chasing CSR kernels there
-    const double pad_ok = (avg <= 8.0) ? 3.0 : 1.25;
-    if (tot < INT32_MAX && (double)entries <= pad_ok * (double)std::max<int64_t>(A->nnz, 1) + 4096) {
-      std::vector<int> sc((size_t)std::max<int64_t>(entries, 1), 0);
-      std::vector<double> sv((size_t)std::max<int64_t>(entries, 1), 0.0);
-#pragma omp parallel for schedule(static)
-      for (int64_t i = 0; i < A->n_rows; ++i) {
-        const size_t base = ((size_t)soff[(size_t)(i >> 5)] << 5) + (size_t)(i & 31);
-        const int e0 = rowptr[(size_t)i], n = rowptr[(size_t)i + 1] - e0;
-        for (int k = 0; k < n; ++k) {
-          sc[base + (size_t)k * 32] = col[(size_t)e0 + k];
-          sv[base + (size_t)k * 32] = val[(size_t)e0 + k];
-        }
-      }
-      A->sell_off.alloc(soff.size());
-      A->sell_col.alloc(sc.size());
-      A->sell_val.alloc(sv.size());
-      GSB_CUDA(cudaMemcpy(A->sell_off.p, soff.data(), sizeof(int) * soff.size(), cudaMemcpyHostToDevice));
-      GSB_CUDA(cudaMemcpy(A->sell_col.p, sc.data(), sizeof(int) * sc.size(), cudaMemcpyHostToDevice));
-      GSB_CUDA(cudaMemcpy(A->sell_val.p, sv.data(), sizeof(double) * sv.size(), cudaMemcpyHostToDevice));
-      A->sell_entries = entries;
-      A->sell_ok = true;
-      A->h_sell_off = soff;
-    }
-  }
-  // staged-x-window plan (opt-in at matrix creation time)
-  A->xs_ok = false;
-  if (A->sell_ok && ctx->opt("xstage", "0") == "1") {
-    XStagePlan xp = build_xstage(A->n_rows, rowptr.data(), col.data(), A->h_sell_off.data(), 256, 8, 6144);
-    if (xp.ok) {
-      auto up_i = [&](DevBuf<int> &d, const std::vector<int> &h) {
-        d.alloc(std::max<size_t>(1, h.size()));
-        if (!h.empty()) GSB_CUDA(cudaMemcpy(d.p, h.data(), sizeof(int) * h.size(), cudaMemcpyHostToDevice));
-      };
-      up_i(A->xs_chunk_seg_ptr, xp.chunk_seg_ptr);
-      up_i(A->xs_seg_start, xp.seg_start);
-      up_i(A->xs_seg_len, xp.seg_len);
-      up_i(A->xs_seg_off, xp.seg_off);
-      A->xs_lcol.alloc(xp.lcol.size());
-      GSB_CUDA(cudaMemcpy(A->xs_lcol.p, xp.lcol.data(), sizeof(unsigned short) * xp.lcol.size(), cudaMemcpyHostToDevice));
-      A->xs_max_window = xp.max_window;
-      A->xs_ok = true;
-    }
-  }
-  // interior / boundary slice lists (only for matrices with ghost columns)
-  A->split_ok = false;
-  if (A->sell_ok && A->n_ghost_cols > 0) {
-    std::vector<int> isl, bsl;
-    const int64_t nsl = (A->n_rows + 31) / 32;
-    for (int64_t sl = 0; sl < nsl; ++sl) {
-      bool bnd = false;
-      for (int64_t i = sl * 32; i < std::min<int64_t>(A->n_rows, sl * 32 + 32) && !bnd; ++i) {
-        const int e0 = rowptr[(size_t)i], e1 = rowptr[(size_t)i + 1];
-        bnd = e1 > e0 && col[(size_t)e1 - 1] >= A->n_own_cols;  // columns ascend: ghosts are last
-      }
-      (bnd ? bsl : isl).push_back((int)sl);
-    }
-    A->n_int_slices = (int64_t)isl.size();
-    A->n_bnd_slices = (int64_t)bsl.size();
-    A->int_slices.alloc(std::max<size_t>(1, isl.size()));
-    A->bnd_slices.alloc(std::max<size_t>(1, bsl.size()));
-    if (!isl.empty()) GSB_CUDA(cudaMemcpy(A->int_slices.p, isl.data(), sizeof(int) * isl.size(), cudaMemcpyHostToDevice));
-    if (!bsl.empty()) GSB_CUDA(cudaMemcpy(A->bnd_slices.p, bsl.data(), sizeof(int) * bsl.size(), cudaMemcpyHostToDevice));
-    A->split_ok = true;
-  }
-  // persistent-CTA row partition balanced by nnz
-  const int rows_per_step = ST_THREADS / A->G;
-  int n_ctas = (int)std::min<int64_t>(ctx->num_sms, std::max<int64_t>(1, (A->n_rows + rows_per_step - 1) / rows_per_step));
-  std::vector<int> cta_rows((size_t)n_ctas + 1, 0);
-  for (int b = 1; b < n_ctas; ++b) {
-    const int64_t target = (int64_t)((double)A->nnz * b / n_ctas);
-    auto it = std::lower_bound(rowptr.begin(), rowptr.end(), (int)target);
-    int r = (int)(it - rowptr.begin());
-    r = std::min<int>(r, (int)A->n_rows);
-    cta_rows[(size_t)b] = std::max(r, cta_rows[(size_t)b - 1]);
-  }
-  cta_rows[(size_t)n_ctas] = (int)A->n_rows;
-  A->n_ctas = n_ctas;
-  A->cta_rows.alloc(cta_rows.size());
-  GSB_CUDA(cudaMemcpy(A->cta_rows.p, cta_rows.data(), sizeof(int) * cta_rows.size(), cudaMemcpyHostToDevice));
-}
-
-int gsb_mat_create(gsb_ctx_t ctx, int64_t n_rows, int64_t n_own_cols, int64_t n_ghost_cols, int fmt, int index_base,
-                   int index_bytes, const void *ptr, const void *idx, const double *vals, gsb_plan_t plan,
-                   gsb_mat_t *out) {
-  GSB_NULLCHK(ctx)
-  API_BEGIN
-  GSB_CHECK(index_bytes == 4 || index_bytes == 8, "mat: index_bytes must be 4 or 8");
-  GSB_CHECK(fmt == GSB_FMT_CSR || fmt == GSB_FMT_CSC, "mat: unknown format");
-  GSB_CHECK(n_ghost_cols == 0 || ctx->nranks == 1 || plan != nullptr, "mat: ghost columns need an exchange plan");
-  const int64_t n_cols = n_own_cols + n_ghost_cols;
-  GSB_CHECK(n_rows < INT32_MAX && n_cols < INT32_MAX, "mat: local dimensions exceed int32");
-  std::unique_ptr<gsb_mat_s> A(new gsb_mat_s());
-  A->ctx = ctx; A->n_rows = n_rows; A->n_own_cols = n_own_cols; A->n_ghost_cols = n_ghost_cols; A->plan = plan;
-  const int64_t nptr = (fmt == GSB_FMT_CSR ? n_rows : n_cols);
-  const int64_t nnz = rd_idx(ptr, index_bytes, nptr) - rd_idx(ptr, index_bytes, 0);
-  GSB_CHECK(nnz >= 0 && nnz < INT32_MAX - 8, "mat: local nnz exceeds int32");
-  const int64_t p0 = rd_idx(ptr, index_bytes, 0);
-  std::vector<int> rowptr((size_t)n_rows + 1, 0), col((size_t)nnz);
-  std::vector<double> val((size_t)nnz);
-  if (fmt == GSB_FMT_CSR) {
-    bool sorted = true;
-    for (int64_t i = 0; i <= n_rows; ++i) rowptr[(size_t)i] = (int)(rd_idx(ptr, index_bytes, i) - p0);
-    for (int64_t e = 0; e < nnz; ++e) {
-      int64_t c = rd_idx(idx, index_bytes, e) - index_base;
-      GSB_CHECK(c >= 0 && c < n_cols, "mat: column index out of range");
-      col[(size_t)e] = (int)c;
-      val[(size_t)e] = vals[e];
-    }
-    for (int64_t i = 0; i < n_rows && sorted; ++i)
-      for (int e = rowptr[(size_t)i] + 1; e < rowptr[(size_t)i + 1]; ++e)
-        if (col[(size_t)e] <= col[(size_t)e - 1]) { sorted = false; break; }
-    if (!sorted) {
-      A->perm.resize((size_t)nnz);
-      std::iota(A->perm.begin(), A->perm.end(), (int64_t)0);
-      for (int64_t i = 0; i < n_rows; ++i)
-        std::sort(A->perm.begin() + rowptr[(size_t)i], A->perm.begin() + rowptr[(size_t)i + 1],
-                  [&](int64_t a, int64_t b) { return col[(size_t)a] < col[(size_t)b]; });
-      std::vector<int> c2((size_t)nnz);
-      std::vector<double> v2((size_t)nnz);
-      for (int64_t e = 0; e < nnz; ++e) { c2[(size_t)e] = col[(size_t)A->perm[(size_t)e]]; v2[(size_t)e] = val[(size_t)A->perm[(size_t)e]]; }
-      col.swap(c2); val.swap(v2);
-    }
-  } else {  // CSC -> CSR; visiting columns in ascending order leaves every row sorted
-    A->perm.resize((size_t)nnz);
-    for (int64_t e = 0; e < nnz; ++e) {
-      int64_t r = rd_idx(idx, index_bytes, e) - index_base;
-      GSB_CHECK(r >= 0 && r < n_rows, "mat: row index out of range");
-      rowptr[(size_t)r + 1]++;
-    }
-    for (int64_t i = 0; i < n_rows; ++i) rowptr[(size_t)i + 1] += rowptr[(size_t)i];
-    std::vector<int> fillp(rowptr.begin(), rowptr.end() - 1);
-    for (int64_t j = 0; j < n_cols; ++j) {
-      const int64_t a = rd_idx(ptr, index_bytes, j) - p0, b = rd_idx(ptr, index_bytes, j + 1) - p0;
-      for (int64_t e = a; e < b; ++e) {
-        const int64_t r = rd_idx(idx, index_bytes, e) - index_base;
-        const int pos = fillp[(size_t)r]++;
-        col[(size_t)pos] = (int)j;
-        val[(size_t)pos] = vals[e];
-        A->perm[(size_t)pos] = e;
-      }
-    }
-  }
-  finish_matrix(A.get(), rowptr, col, val);
-  *out = A.release();
-  API_END(ctx)
-}
-
-int gsb_mat_update_values(gsb_mat_t A, const double *vals) {
-  GSB_NULLCHK(A)
-  API_BEGIN
-  GSB_CHECK(A->nb == 0, "update_values: block matrix");
-  std::vector<double> v((size_t)A->nnz);
-  for (int64_t e = 0; e < A->nnz; ++e) v[(size_t)e] = A->perm.empty() ? vals[e] : vals[A->perm[(size_t)e]];
-  if (A->nnz) GSB_CUDA(cudaMemcpy(A->val.p, v.data(), sizeof(double) * A->nnz, cudaMemcpyHostToDevice));
-  if (A->sell_ok) {
-    std::vector<int> rp((size_t)A->n_rows + 1);
-    GSB_CUDA(cudaMemcpy(rp.data(), A->rowptr.p, sizeof(int) * rp.size(), cudaMemcpyDeviceToHost));
-    std::vector<double> sv((size_t)std::max<int64_t>(A->sell_entries, 1), 0.0);
-    for (int64_t i = 0; i < A->n_rows; ++i) {
-      const size_t base = ((size_t)A->h_sell_off[(size_t)(i >> 5)] << 5) + (size_t)(i & 31);
-      const int e0 = rp[(size_t)i], n = rp[(size_t)i + 1] - e0;
-      for (int k = 0; k < n; ++k) sv[base + (size_t)k * 32] = v[(size_t)e0 + k];
-    }
-    GSB_CUDA(cudaMemcpy(A->sell_val.p, sv.data(), sizeof(double) * sv.size(), cudaMemcpyHostToDevice));
-  }
-  API_END(A->ctx)
-}
-
-int gsb_mat_info(gsb_mat_t A, int64_t *n_rows, int64_t *n_own_cols, int64_t *n_ghost_cols, int64_t *nnz) {
-  GSB_NULLCHK(A)
-  if (n_rows) *n_rows = A->n_rows;
-  if (n_own_cols) *n_own_cols = A->n_own_cols;
-  if (n_ghost_cols) *n_ghost_cols = A->n_ghost_cols;
-  if (nnz) *nnz = A->nnz;
-  return GSB_OK;
-}
-
-int gsb_mat_destroy(gsb_mat_t A) {
-  delete A;
-  return GSB_OK;
-}
-
-int gsb_block_mat_create(gsb_ctx_t ctx, int nb, const gsb_mat_t *blocks, gsb_mat_t *out) {
-  GSB_NULLCHK(ctx)
-  API_BEGIN
-  GSB_CHECK(nb >= 1, "block matrix: nb < 1");
-  std::unique_ptr<gsb_mat_s> A(new gsb_mat_s());
-  A->ctx = ctx; A->nb = nb;
-  A->blocks.assign(blocks, blocks + (size_t)nb * nb);
-  std::vector<int64_t> rs((size_t)nb, -1), cs((size_t)nb, -1);
-  for (int i = 0; i < nb; ++i)
-    for (int j = 0; j < nb; ++j) {
-      gsb_mat_t B = A->blocks[(size_t)i * nb + j];
-      if (!B) continue;
-      GSB_CHECK(B->n_ghost_cols == 0, "block matrix: distributed blocks not supported");
-      GSB_CHECK(rs[(size_t)i] < 0 || rs[(size_t)i] == B->n_rows, "block matrix: inconsistent block rows");
-      GSB_CHECK(cs[(size_t)j] < 0 || cs[(size_t)j] == B->n_own_cols, "block matrix: inconsistent block cols");
-      rs[(size_t)i] = B->n_rows; cs[(size_t)j] = B->n_own_cols;
-      A->nnz += B->nnz;
-    }
-  A->row_off.assign((size_t)nb + 1, 0); A->col_off.assign((size_t)nb + 1, 0);
-  for (int i = 0; i < nb; ++i) {
-    GSB_CHECK(rs[(size_t)i] >= 0 && cs[(size_t)i] >= 0, "block matrix: empty block row/column");
-    A->row_off[(size_t)i + 1] = A->row_off[(size_t)i] + rs[(size_t)i];
-    A->col_off[(size_t)i + 1] = A->col_off[(size_t)i] + cs[(size_t)i];
-  }
-  A->n_rows = A->row_off.back(); A->n_own_cols = A->col_off.back();
-  *out = A.release();
-  API_END(ctx)
-}
-
 // ---------------------------------------------------------------- vectors
 int gsb_vec_create(gsb_ctx_t ctx, int64_t n_own, int64_t n_ghost, gsb_vec_t *out) {
   GSB_NULLCHK(ctx)
@@ -1383,6 +1155,30 @@ int gsb_vec_consistent(gsb_vec_t v, gsb_plan_t plan) {
   gsb::consistent(*v, plan);
   GSB_CUDA(cudaStreamSynchronize(v->ctx->stream));
   API_END(v->ctx)
+}
+
+int gsb_vec_assemble(gsb_vec_t v, gsb_plan_t plan) {
+  GSB_NULLCHK(v)
+  API_BEGIN
+  gsb::assemble(*v, plan);
+  GSB_CUDA(cudaStreamSynchronize(v->ctx->stream));
+  API_END(v->ctx)
+}
+
+// page-lock a caller-owned host buffer (a Julia Vector{Float64}) so that gsb_solve_host / gsb_vec_set / gsb_vec_get
+// copy at pinned-memory speed
+int gsb_host_register(gsb_ctx_t ctx, void *ptr, int64_t bytes) {
+  GSB_NULLCHK(ctx)
+  API_BEGIN
+  GSB_CHECK(ptr != nullptr && bytes > 0, "host_register: bad arguments");
+  GSB_CUDA(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+  API_END(ctx)
+}
+int gsb_host_unregister(gsb_ctx_t ctx, void *ptr) {
+  GSB_NULLCHK(ctx)
+  API_BEGIN
+  GSB_CUDA(cudaHostUnregister(ptr));
+  API_END(ctx)
 }
 
 // ---------------------------------------------------------------- primitives

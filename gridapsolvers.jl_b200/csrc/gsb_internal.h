@@ -77,9 +77,11 @@ struct gsb_ctx_s {
   // device scalars + reduction scratch
   gsb::DevBuf<double> scal;
   int next_slot = 8;  // slots 0..7: scratch for the C-ABI dot/norm calls
+  std::vector<std::pair<int, int>> free_ranges;  // (start, count) of slot ranges returned by destroyed solvers
   gsb::DevBuf<double> partials;
   gsb::DevBuf<unsigned int> ticket;
-  double *h_scal = nullptr;  // pinned host mirror for read-backs
+  double *h_scal = nullptr;  // pinned host mirror for read-backs: H_SCAL_READ slots + one staging word
+  static constexpr int H_SCAL_READ = 4096;
   std::map<std::string, std::string> opts;
   std::string err;
   // a caller that already knows ||b|| on the host (CG knows ||r||, GMRES knows ||V_j|| = 1) tells the
@@ -92,6 +94,7 @@ struct gsb_ctx_s {
   bool profiling = false;
   std::vector<ProfRec> prof;
   int alloc_slots(int n);
+  void free_slots(int start, int n);
   double read_scalar(int slot);                 // blocking
   void read_scalars(int slot, int n, double *out);
   void allreduce_slot(int slot, int n = 1);     // in-place NCCL allreduce when nranks > 1
@@ -137,34 +140,28 @@ struct gsb_vec_s {
 
 struct gsb_mat_s {
   gsb_ctx_t ctx;
-  int64_t n_rows = 0, n_own_cols = 0, n_ghost_cols = 0, nnz = 0, nnz_padded = 0;
+  int64_t n_rows = 0, n_own_cols = 0, n_ghost_cols = 0, nnz = 0;
   gsb_plan_t plan = nullptr;
+  // CSR mirror: row pointers always; column ids / values only for small matrices and for matrices that have
+  // no block-SELL form (the row kernels of large matrices stream the block-SELL arrays only)
   gsb::DevBuf<int> rowptr, col;
   gsb::DevBuf<double> val;
+  bool csr_kept = false;
+  gsb::DevBuf<double> diag;  // diag(A_own_own), 0 for a missing entry (JacobiLinearSolvers.jl:20-23)
+  gsb::DevBuf<int> diag_pos; // CSR position of each row's diagonal entry (-1: none), for value refreshes
   // upload permutation: position in the caller's value array of each CSR entry (for update_values)
   std::vector<int64_t> perm;  // empty == identity
   int max_row_nnz = 0;
-  int G = 1;  // lanes per row
-  // streaming kernel partition
-  bool stream_ok = false;
-  int n_ctas = 0;
-  gsb::DevBuf<int> cta_rows;
-  // SELL-32 mirror (column-major slices of 32 rows), built when padding overhead is small
+  int G = 1;  // lanes per row of the CSR fallback kernel
+  // block-SELL-32 (kernels.cuh sell_kernel): BS x BS blocks, one lane per block row, optional sorting of
+  // the block rows by length inside windows of 256
   bool sell_ok = false;
-  int64_t sell_entries = 0;  // incl. padding
-  gsb::DevBuf<int> sell_off, sell_col;
-  std::vector<int> h_sell_off;
+  int bs = 1;
+  bool sorted = false;
+  int64_t n_brows = 0, n_slices = 0;
+  int64_t sell_blocks = 0;  // stored blocks incl. padding
+  gsb::DevBuf<int> sell_perm, sell_blen, sell_off, sell_bcol;
   gsb::DevBuf<double> sell_val;
-  // staged-x-window variant (xstage.h; opt-in, round-2 work item)
-  bool xs_ok = false;
-  int xs_max_window = 0;
-  gsb::DevBuf<unsigned short> xs_lcol;
-  gsb::DevBuf<int> xs_chunk_seg_ptr, xs_seg_start, xs_seg_len, xs_seg_off;
-  // L2-pipelined multi-sweep smoother (kernels.cuh sell_pipe_kernel)
-  int64_t bw_rows = 0;  // max |col - row| over the own columns
-  gsb::DevBuf<unsigned int> pipe_ctr;  // [ticket, exited]
-  gsb::DevBuf<int> pipe_prefix, pipe_done;
-  int pipe_epoch = 0;
   // halo overlap: slices whose rows touch no ghost column ("interior") run while the exchange is in
   // flight, the remaining ("boundary") slices after it
   bool split_ok = false;
@@ -174,6 +171,8 @@ struct gsb_mat_s {
   int nb = 0;
   std::vector<gsb_mat_t> blocks;  // row-major nb*nb, may contain nullptr
   std::vector<int64_t> row_off, col_off;
+  // bytes the row kernels stream per pass over the matrix (values + ids + per-row metadata)
+  int64_t format_bytes() const;
 };
 
 namespace gsb {
@@ -224,5 +223,8 @@ struct gsb_solver_s {
   virtual const char *name() const = 0;
   virtual gsb_mat_t matrix() { return nullptr; }       // the system matrix, when the solver has one
   virtual void finish() {}                             // resolve a deferred (device-resident) log
+  // true when solve() only enqueues device work (no host read-back, no data-dependent host control flow),
+  // i.e. it may run inside a CUDA-graph capture
+  virtual bool capturable() const { return false; }
   std::unique_ptr<gsb_vec_s> host_x, host_b;           // staging for gsb_solve_host
 };

@@ -181,13 +181,25 @@ __device__ __forceinline__ void row_epilogue_pre(const RowArgs &a, int64_t row, 
 }
 
 // ------------------------------------------------------------------------------------------
-// SELL-32 kernel: the matrix is also kept in sliced-ELLPACK form with slice height 32 (one warp =
-// one slice, one lane = one row, entries of a slice stored column-major: entry k of the 32 rows
-// is contiguous).  Every matrix load of a warp is then one fully coalesced 256 B (values) /
-// 128 B (columns) transaction with addresses known in advance -- no row-pointer -> data
-// dependence, no shared-memory staging, no barriers -- and with one lane per row the gathers of x
-// are coalesced too and the row sum keeps the sequential ascending-column order (bit-exact with
-// the oracle).  Matrix data is streamed with L1::no_allocate so that L1 keeps x.
+// Block-SELL-32 row kernel (the hot kernel of every configuration).
+//
+// Storage (built on the device from the uploaded CSR arrays, sell_fill_kernel below):
+//   * rows are grouped in BLOCK ROWS of BS consecutive rows (BS = 1, 2, 3: the DOF block of a
+//     node-major vector-valued FE space; BS = 1 for scalar problems and for any matrix whose sparsity is
+//     not made of aligned BS x BS blocks).  One lane owns one block row, one warp owns one SLICE of 32
+//     block rows, the blocks of a slice are stored column-major: block k of the 32 lanes is contiguous
+//     (one 128 B line of block-column ids, BS*BS 256 B lines of values) -- every matrix load of a warp is
+//     a fully coalesced transaction whose address does not depend on a row pointer.
+//   * slice width = longest block row of the slice.  When consecutive rows have very different lengths
+//     (Q2 elements: 125/75/45/27-node stencils alternate along a mesh line) the block rows are sorted by
+//     length inside windows of 256 block rows (SELL-C-sigma with C = 32, sigma = 256) and `perm` maps a
+//     (slice, lane) position to its block row; padding lanes have perm = -1.
+//   * bytes per stored non-zero: 8 + 4/BS^2 (value + shared block-column id) instead of CSR's 12.
+// Arithmetic: lane-sequential, ascending column order inside every row, product rounded before the add
+// (__dmul_rn/__dadd_rn) -- row i of a block row visits block k = 0,1,.. and inside a block column
+// j = 0..BS-1, i.e. exactly the CSR order of that row => bit-identical to the oracle's sequential CSR
+// loop for every BS and with or without the permutation.  Matrix data is streamed with L1::no_allocate
+// so that L1 keeps the gathered vector.
 __device__ __forceinline__ double ldg_stream_f64(const double *p) {
   double v;
   asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
@@ -198,488 +210,110 @@ __device__ __forceinline__ int ldg_stream_s32(const int *p) {
   asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
+__device__ __forceinline__ double ldg_nc_f64(const double *p) {
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
 
 struct SellArgs {
   const int *slice_list;  // optional indirection: the slices this launch processes (nullptr = all)
   int64_t n_list;         // number of slices this launch processes
-  const int *rowptr;      // CSR row pointers (row lengths)
-  const int *slice_off;   // per slice: offset of the slice in units of 32 entries; nslices+1 entries
-  const int *col;         // padded, column-major per slice
-  const double *val;
-  int64_t nrows;
+  const int *perm;        // PERM only: block row of every (slice, lane) position, -1 = padding lane
+  const int *blen;        // blocks per block row, indexed by position (padded with 0)
+  const int *slice_off;   // per slice: offset of the slice in units of 32 blocks; nslices+1 entries
+  const int *bcol;        // block-column ids, column-major per slice
+  const double *val;      // BS*BS values per block, each (k, i, j) a 32-lane line
+  int64_t n_brows;        // number of block rows
 };
 
-template <int MODE, int THREADS, int U, int MINB = 1, int STYLE = 0>
-__global__ void __launch_bounds__(THREADS, MINB) csr_sell_kernel(SellArgs m, RowArgs a) {
+template <int MODE, int BS, bool PERM, int THREADS, int U, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) sell_kernel(SellArgs m, RowArgs a) {
   __shared__ double red_smem[THREADS / 32];
+  constexpr int BB = BS * BS;
   const int64_t widx = ((int64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;  // one warp per slice
   const int lane = threadIdx.x & 31;
   double acc = 0.0;
   if (widx < m.n_list) {  // warp-uniform
     const int64_t slice = m.slice_list ? (int64_t)m.slice_list[widx] : widx;
-    const int64_t row = (slice << 5) + lane;
-    const bool valid = row < m.nrows;
-    const int so0 = m.slice_off[slice], so1 = m.slice_off[slice + 1];
-    const int width = so1 - so0;  // entries per row in this slice (warp-uniform)
-    int len = 0;
-    RowPre<MODE> pre{};
-    double s = 0.0;
-    if (valid) {
-      len = m.rowptr[row + 1] - m.rowptr[row];
-      row_prefetch<MODE>(a, row, pre);
-      s = row_init<MODE>(a, row);
+    const int64_t pos = (slice << 5) + lane;
+    int64_t brow = pos;
+    bool valid;
+    if (PERM) {
+      const int p = m.perm[pos];
+      brow = p;
+      valid = p >= 0;
+    } else {
+      valid = pos < m.n_brows;
     }
-    const size_t base = ((size_t)so0 << 5) + lane;
-    const int *cp = m.col + base;
-    const double *vp = m.val + base;
+    const int len = m.blen[pos];
+    const int so0 = m.slice_off[slice], so1 = m.slice_off[slice + 1];
+    const int width = so1 - so0;  // blocks per lane in this slice (warp-uniform)
+    RowPre<MODE> pre{};
+    double s[BS];
+#pragma unroll
+    for (int i = 0; i < BS; ++i) s[i] = 0.0;
+    if (valid) {
+      if (BS == 1) row_prefetch<MODE>(a, brow, pre);
+#pragma unroll
+      for (int i = 0; i < BS; ++i) s[i] = row_init<MODE>(a, brow * BS + i);
+    }
+    const int *cp = m.bcol + ((size_t)so0 << 5) + lane;
+    const double *vp = m.val + (((size_t)so0 * BB) << 5) + lane;
     const double al = a.alpha;
     int k = 0;
     for (; k + U <= width; k += U) {
       int cc[U];
-      double vv[U], xv[U];
-      if (STYLE == 0) {
+      double vv[U][BB], xv[U][BS];
+      // burst order: all block-column ids, then all values (contiguous bursts per warp), then the gathers
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          cc[u] = ldg_stream_s32(cp + (size_t)(k + u) * 32);
-          vv[u] = ldg_stream_f64(vp + (size_t)(k + u) * 32);
-        }
+      for (int u = 0; u < U; ++u) cc[u] = ldg_stream_s32(cp + (size_t)(k + u) * 32);
 #pragma unroll
-        for (int u = 0; u < U; ++u) xv[u] = __ldg(a.x + cc[u]);
-      } else {
-        // burst order: all column ids, then all values (two contiguous bursts per warp), then the gathers
+      for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int u = 0; u < U; ++u) cc[u] = ldg_stream_s32(cp + (size_t)(k + u) * 32);
+        for (int e = 0; e < BB; ++e) vv[u][e] = ldg_stream_f64(vp + ((size_t)(k + u) * BB + e) * 32);
 #pragma unroll
-        for (int u = 0; u < U; ++u) vv[u] = ldg_stream_f64(vp + (size_t)(k + u) * 32);
+      for (int u = 0; u < U; ++u) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          double t;
-          asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(t) : "l"(a.x + cc[u]));
-          xv[u] = t;
-        }
+        for (int j = 0; j < BS; ++j) xv[u][j] = ldg_nc_f64(a.x + (size_t)cc[u] * BS + j);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (k + u < len) {
-          double t = xv[u];
-          if (MODE == ROW_SPMV) t = __dmul_rn(t, al);
-          s = __dadd_rn(s, __dmul_rn(vv[u], t));
+          double t[BS];
+#pragma unroll
+          for (int j = 0; j < BS; ++j) t[j] = (MODE == ROW_SPMV) ? __dmul_rn(xv[u][j], al) : xv[u][j];
+#pragma unroll
+          for (int i = 0; i < BS; ++i)
+#pragma unroll
+            for (int j = 0; j < BS; ++j) s[i] = __dadd_rn(s[i], __dmul_rn(vv[u][i * BS + j], t[j]));
         }
       }
     }
     for (; k < width; ++k) {
       const int c = ldg_stream_s32(cp + (size_t)k * 32);
-      const double v = ldg_stream_f64(vp + (size_t)k * 32);
-      double t = __ldg(a.x + c);
+      double vv[BB], xv[BS];
+#pragma unroll
+      for (int e = 0; e < BB; ++e) vv[e] = ldg_stream_f64(vp + ((size_t)k * BB + e) * 32);
+#pragma unroll
+      for (int j = 0; j < BS; ++j) xv[j] = ldg_nc_f64(a.x + (size_t)c * BS + j);
       if (k < len) {
-        if (MODE == ROW_SPMV) t = __dmul_rn(t, al);
-        s = __dadd_rn(s, __dmul_rn(v, t));
+#pragma unroll
+        for (int j = 0; j < BS; ++j)
+          if (MODE == ROW_SPMV) xv[j] = __dmul_rn(xv[j], al);
+#pragma unroll
+        for (int i = 0; i < BS; ++i)
+#pragma unroll
+          for (int j = 0; j < BS; ++j) s[i] = __dadd_rn(s[i], __dmul_rn(vv[i * BS + j], xv[j]));
       }
     }
-    if (valid) row_epilogue_pre<MODE>(a, row, s, pre, acc);
-  }
-  if (MODE == ROW_SPMV_DOT) {
-    double v[1] = {acc};
-    grid_reduce_finish<THREADS, 1>(v, a.red, red_smem);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// L2-pipelined Jacobi-Richardson sweeps: S consecutive sweeps of the smoother in ONE launch, so that
-// the matrix is streamed from HBM once and re-read S-1 times from the 126 MB L2.
-//
-// Work item = (stage j, chunk c of 256 rows).  Items are handed out in the order
-//     tau = 0,1,2,... ; j = 0..S-1 ; c = tau - j*LAG
-// i.e. stage j trails stage j-1 by LAG chunks.  Stage j of chunk c gathers dx produced by stage j-1
-// on chunks [c-reach, c+reach] (reach = matrix bandwidth in chunks) and overwrites the dx buffer that
-// stage j-1 itself gathered from, so it may start only when stage j-1 has completed every chunk up
-// to c+reach: one monotone counter per stage (`prefix[j]` = number of leading chunks completed)
-// carries both the RAW and the WAR dependency.  LAG > reach + (items in flight)/S makes the wait
-// almost never spin, and every dependency of an item has a smaller ticket, so persistent CTAs that
-// take tickets in order can never deadlock.  Arithmetic per row is exactly that of ROW_SWEEP /
-// ROW_RESID (same order, same roundings): the result is bit-identical to S separate launches.
-// Vectors written inside the kernel are read with ld.global.cg (L2) -- L1 is not coherent.
-// matrix loads with an L2 cache-policy hint (createpolicy): evict_last while a later pipeline stage will
-// re-read the line, evict_first on its final use
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-__device__ __forceinline__ double ldg_hint_f64(const double *p, uint64_t pol) {
-  double v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
-  return v;
-}
-__device__ __forceinline__ int ldg_hint_s32(const int *p, uint64_t pol) {
-  int v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
-  return v;
-}
-
-struct PipeArgs {
-  SellArgs m;
-  double *r, *x;
-  const double *invd;
-  double *dxbuf[2];
-  double omega;
-  int k0;        // global index (1-based) of the sweep stage 0 performs
-  int S;         // stages in this launch
-  int niter;     // total sweeps of the smoother application: sweep niter only updates r
-  int nchunks, lag, reach;
-  unsigned int *ticket;  // work counter (zero at launch; reset by the last CTA)
-  unsigned int *exited;
-  int *prefix;   // S counters, zero at launch
-  int *done;     // S * nchunks flags, compared against epoch
-  int epoch;
-  int l2_hints;  // use L2 eviction-priority hints on the matrix stream
-};
-
-template <int THREADS, int U>
-__global__ void __launch_bounds__(THREADS, 4) sell_pipe_kernel(PipeArgs p) {
-  __shared__ unsigned int s_t[2];
-  __shared__ int s_lo;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned int total = (unsigned int)(p.nchunks + (p.S - 1) * p.lag) * (unsigned int)p.S;
-  if (threadIdx.x == 0) s_t[0] = atomicAdd(p.ticket, 1u);
-  const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
-  int it = 0;
-  for (;; ++it) {
-    __syncthreads();
-    const unsigned int t = s_t[it & 1];
-    if (t >= total) break;
-    // take the next ticket now: its latency overlaps this item's work
-    if (threadIdx.x == 0) s_t[(it + 1) & 1] = atomicAdd(p.ticket, 1u);
-    const int tau = (int)(t / (unsigned int)p.S), j = (int)(t % (unsigned int)p.S);
-    const int c = tau - j * p.lag;
-    if (c < 0 || c >= p.nchunks) continue;
-    if (j > 0) {
-      // stage j-1 must have completed every chunk below `need`: start from the published lower
-      // bound and check the completion flags of the remaining chunks with the whole CTA
-      const int need = min(p.nchunks, c + p.reach + 1);
-      int *pf = p.prefix + (j - 1);
-      const int *dn = p.done + (size_t)(j - 1) * p.nchunks;
-      const long long t0 = clock64();
-      for (;;) {
-        // one thread reads the lower bound: every thread must scan from the SAME value, or the
-        // strided scans would leave holes
-        if (threadIdx.x == 0) {
-          int v;
-          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(pf) : "memory");
-          s_lo = v;
-        }
-        __syncthreads();
-        const int lo = s_lo;
-        bool ok = true;
-        for (int q = lo + (int)threadIdx.x; q < need; q += THREADS) {
-          int fl;
-          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(fl) : "l"(dn + q) : "memory");
-          ok = ok && (fl == p.epoch);
-        }
-        if (__syncthreads_and(ok)) {
-          if (threadIdx.x == 0 && need > lo) atomicMax(pf, need);
-          break;
-        }
-        if (clock64() - t0 > 20000000000LL) __trap();
-        __nanosleep(200);
-      }
-    }
-    // a later stage re-reads this chunk's matrix rows -> ask L2 to keep them; final use -> evict first
-    const uint64_t pol = (j + 1 < p.S) ? pol_keep : pol_drop;
-    const int k = p.k0 + j;            // sweep index
-    const bool last = (k == p.niter);  // the final sweep only updates the residual
-    const double *xin = p.dxbuf[(k - 1) & 1];
-    double *dxout = p.dxbuf[k & 1];
-    const int64_t slice = (int64_t)c * (THREADS / 32) + warp;
-    const int64_t nslices = (p.m.nrows + 31) >> 5;
-    if (slice < nslices) {
-      const int64_t row = (slice << 5) + lane;
-      const bool valid = row < p.m.nrows;
-      const int so0 = p.m.slice_off[slice], so1 = p.m.slice_off[slice + 1];
-      const int width = so1 - so0;
-      int len = 0;
-      double rb = 0.0, idg = 0.0, xa = 0.0, s = 0.0;
-      if (valid) {
-        len = p.m.rowptr[row + 1] - p.m.rowptr[row];
-        rb = __ldcg(p.r + row);
-        if (!last) { idg = __ldg(p.invd + row); xa = __ldcg(p.x + row); }
-      }
-      const size_t base = ((size_t)so0 << 5) + lane;
-      const int *cp = p.m.col + base;
-      const double *vp = p.m.val + base;
-      int kk = 0;
-      for (; kk + U <= width; kk += U) {
-        int cc[U];
-        double vv[U], xv[U];
-        if (p.l2_hints) {
-#pragma unroll
-          for (int u = 0; u < U; ++u) cc[u] = ldg_hint_s32(cp + (size_t)(kk + u) * 32, pol);
-#pragma unroll
-          for (int u = 0; u < U; ++u) vv[u] = ldg_hint_f64(vp + (size_t)(kk + u) * 32, pol);
-        } else {
-#pragma unroll
-          for (int u = 0; u < U; ++u) cc[u] = ldg_stream_s32(cp + (size_t)(kk + u) * 32);
-#pragma unroll
-          for (int u = 0; u < U; ++u) vv[u] = ldg_stream_f64(vp + (size_t)(kk + u) * 32);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) xv[u] = __ldcg(xin + cc[u]);
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-          if (kk + u < len) s = __dadd_rn(s, __dmul_rn(vv[u], xv[u]));
-      }
-      for (; kk < width; ++kk) {
-        const int cidx = ldg_stream_s32(cp + (size_t)kk * 32);
-        const double v = ldg_stream_f64(vp + (size_t)kk * 32);
-        const double tx = __ldcg(xin + cidx);
-        if (kk < len) s = __dadd_rn(s, __dmul_rn(v, tx));
-      }
-      if (valid) {
-        const double rn = __dsub_rn(rb, s);
-        p.r[row] = rn;
-        if (!last) {
-          const double d = __dmul_rn(p.omega, __dmul_rn(idg, rn));
-          dxout[row] = d;
-          p.x[row] = __dadd_rn(xa, d);
-        }
-      }
-    }
-    // publish: every thread's stores first (fence), then this chunk's completion flag
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0)
-      asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.done + (size_t)j * p.nchunks + c), "r"(p.epoch) : "memory");
-  }
-  // the last CTA to leave resets the counters for the next launch
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    if (atomicAdd(p.exited, 1u) == gridDim.x - 1) {
-      *p.ticket = 0u;
-      *p.exited = 0u;
-      for (int j = 0; j < p.S; ++j) p.prefix[j] = 0;
-      __threadfence();
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// SELL-32 with a staged x window (opt-in `xstage=1`; planner in xstage.h, NOT yet validated on hardware --
-// round-2 work item 1).  One CTA = one chunk of THREADS rows: the contiguous column segments the chunk
-// references are copied from the gathered vector into shared memory, the per-entry column id is a 16-bit
-// offset into that window, and the row loop gathers from shared memory.  Same accumulation order as
-// csr_sell_kernel (bit-identical results).
-struct XStageArgs {
-  const int *rowptr;
-  const int *slice_off;
-  const unsigned short *lcol;   // SELL layout, window offsets
-  const double *val;            // SELL layout
-  const int *chunk_seg_ptr;     // nchunks + 1
-  const int *seg_start, *seg_len, *seg_off;
-  int64_t nrows;
-};
-__device__ __forceinline__ unsigned short ldg_stream_u16(const unsigned short *p) {
-  unsigned short v;
-  asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
-  return v;
-}
-
-template <int MODE, int THREADS, int U>
-__global__ void __launch_bounds__(THREADS, 4) csr_sell_xs_kernel(XStageArgs m, RowArgs a) {
-  extern __shared__ double xwin[];
-  __shared__ double red_smem[THREADS / 32];
-  const int chunk = blockIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // stage the window: segment after segment, coalesced
-  const int sg0 = m.chunk_seg_ptr[chunk], sg1 = m.chunk_seg_ptr[chunk + 1];
-  for (int sgi = sg0; sgi < sg1; ++sgi) {
-    const int start = m.seg_start[sgi], len = m.seg_len[sgi], off = m.seg_off[sgi];
-    for (int t = threadIdx.x; t < len; t += THREADS) xwin[off + t] = __ldg(a.x + start + t);
-  }
-  __syncthreads();
-  double acc = 0.0;
-  const int64_t slice = (int64_t)chunk * (THREADS / 32) + warp;
-  const int64_t nslices = (m.nrows + 31) >> 5;
-  if (slice < nslices) {
-    const int64_t row = (slice << 5) + lane;
-    const bool valid = row < m.nrows;
-    const int so0 = m.slice_off[slice], so1 = m.slice_off[slice + 1];
-    const int width = so1 - so0;
-    int len = 0;
-    RowPre<MODE> pre{};
-    double s = 0.0;
     if (valid) {
-      len = m.rowptr[row + 1] - m.rowptr[row];
-      row_prefetch<MODE>(a, row, pre);
-      s = row_init<MODE>(a, row);
-    }
-    const size_t base = ((size_t)so0 << 5) + lane;
-    const unsigned short *cp = m.lcol + base;
-    const double *vp = m.val + base;
-    const double al = a.alpha;
-    int k = 0;
-    for (; k + U <= width; k += U) {
-      unsigned short cc[U];
-      double vv[U];
+      if (BS == 1) {
+        row_epilogue_pre<MODE>(a, brow, s[0], pre, acc);
+      } else {
 #pragma unroll
-      for (int u = 0; u < U; ++u) cc[u] = ldg_stream_u16(cp + (size_t)(k + u) * 32);
-#pragma unroll
-      for (int u = 0; u < U; ++u) vv[u] = ldg_stream_f64(vp + (size_t)(k + u) * 32);
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (k + u < len) {
-          double t = xwin[cc[u]];
-          if (MODE == ROW_SPMV) t = __dmul_rn(t, al);
-          s = __dadd_rn(s, __dmul_rn(vv[u], t));
-        }
+        for (int i = 0; i < BS; ++i) row_epilogue<MODE>(a, brow * BS + i, s[i], acc);
       }
-    }
-    for (; k < width; ++k) {
-      const unsigned short c = ldg_stream_u16(cp + (size_t)k * 32);
-      const double v = ldg_stream_f64(vp + (size_t)k * 32);
-      if (k < len) {
-        double t = xwin[c];
-        if (MODE == ROW_SPMV) t = __dmul_rn(t, al);
-        s = __dadd_rn(s, __dmul_rn(v, t));
-      }
-    }
-    if (valid) row_epilogue_pre<MODE>(a, row, s, pre, acc);
-  }
-  if (MODE == ROW_SPMV_DOT) {
-    double v[1] = {acc};
-    grid_reduce_finish<THREADS, 1>(v, a.red, red_smem);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// PTX helpers: mbarrier + TMA 1-D bulk copy (cp.async.bulk, SASS: UBLKCP)
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-
-// ------------------------------------------------------------------------------------------
-// streaming CSR kernel (the hot kernel): persistent CTAs, each owning a contiguous block of rows
-// (balanced by nnz at set-up time).  One elected thread streams the CTA's slice of val[] / col[]
-// through a shared-memory ring with TMA bulk copies (CHUNK non-zeros per copy, one mbarrier per
-// ring slot); the other threads never touch DRAM for matrix data.  THREADS/G rows are processed
-// per step, G lanes per row walking the row's segment of the ring; gathers of x go through L1/L2.
-//   ring bytes = RING*(8+4); in flight per SM ~ (RING - group span) * 12 B.
-template <int G, int MODE, int THREADS, int RING_LOG2, int CHUNK_LOG2>
-__global__ void __launch_bounds__(THREADS) csr_stream_kernel(StreamArgs m, RowArgs a) {
-  constexpr int RING = 1 << RING_LOG2;
-  constexpr int CHUNK = 1 << CHUNK_LOG2;
-  constexpr int NSLOT = RING / CHUNK;
-  constexpr int ROWS = THREADS / G;
-  constexpr int SPAN_MAX = RING / 2;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  double *sval = reinterpret_cast<double *>(smem_raw);
-  int *scol = reinterpret_cast<int *>(smem_raw + (size_t)RING * 8);
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)RING * 12);
-  __shared__ double red_smem[THREADS / 32];
-
-  const int R0 = m.cta_rows[blockIdx.x], R1 = m.cta_rows[blockIdx.x + 1];
-  double acc = 0.0;
-  if (R0 < R1) {
-    const int E0 = m.rowptr[R0], E1 = m.rowptr[R1];
-    const int S0 = E0 & ~3;  // 16-byte aligned start of this CTA's stream
-    const int nchunks = (E1 - S0 + CHUNK - 1) >> CHUNK_LOG2;
-    if (threadIdx.x == 0) {
-      for (int s = 0; s < NSLOT; ++s) mbar_init(&full[s], 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    int issued = 0;  // next chunk to issue (thread 0 only)
-    const int t_row = threadIdx.x / G, lane = threadIdx.x % G;
-    int g0 = R0;
-    // row pointers of the first group
-    int rp0 = 0, rp1 = 0;
-    {
-      const int r = g0 + t_row;
-      if (r < R1) { rp0 = m.rowptr[r]; rp1 = m.rowptr[r + 1]; }
-    }
-    __shared__ int s_gbase;
-    while (g0 < R1) {
-      if (threadIdx.x == 0) s_gbase = rp0;  // thread 0 holds the row pointer of row g0
-      // barrier #1: the previous group is fully consumed (its ring slots may be refilled) and
-      // the base of this group is published
-      __syncthreads();
-      const int gbase = s_gbase;
-      const bool in_rng = (g0 + t_row < R1);
-      // barrier #2: n = number of rows of this group (row-pointer prefix within SPAN_MAX)
-      const int n = __syncthreads_count(in_rng && lane == 0 && (rp1 - gbase) <= SPAN_MAX);
-      const int clo = (gbase - S0) >> CHUNK_LOG2;
-      if (threadIdx.x == 0) {
-        const int lim = min(nchunks, clo + NSLOT);
-        for (; issued < lim; ++issued) {
-          const int slot = issued & (NSLOT - 1);
-          const int64_t start = (int64_t)S0 + ((int64_t)issued << CHUNK_LOG2);
-          int64_t cnt = m.nnz_padded - start;
-          if (cnt > CHUNK) cnt = CHUNK;
-          mbar_expect_tx(&full[slot], (uint32_t)cnt * 12u);
-          tma_bulk_g2s(sval + (size_t)slot * CHUNK, m.val + start, (uint32_t)cnt * 8u, &full[slot]);
-          tma_bulk_g2s(scol + (size_t)slot * CHUNK, m.col + start, (uint32_t)cnt * 4u, &full[slot]);
-        }
-      }
-      const bool active = (t_row < n);
-      const int e0 = rp0, e1 = rp1;
-      const int64_t row = g0 + t_row;
-      // prefetch the next group's row pointers while this one is processed
-      {
-        const int r = g0 + n + t_row;
-        rp0 = 0; rp1 = 0;
-        if (r < R1) { rp0 = m.rowptr[r]; rp1 = m.rowptr[r + 1]; }
-      }
-      double s = 0.0;
-      if (active) {
-        if (e1 > e0) {
-          const int c0 = (e0 - S0) >> CHUNK_LOG2, c1 = (e1 - 1 - S0) >> CHUNK_LOG2;
-          for (int c = c0; c <= c1; ++c) mbar_wait(&full[c & (NSLOT - 1)], (uint32_t)((c / NSLOT) & 1));
-        }
-        if (lane == 0) s = row_init<MODE>(a, row);
-        const double al = a.alpha;
-#pragma unroll 4
-        for (int e = e0 + lane; e < e1; e += G) {
-          const int p = (e - S0) & (RING - 1);
-          const int c = scol[p];
-          const double v = sval[p];
-          double xv = __ldg(a.x + c);
-          if (MODE == ROW_SPMV) xv = __dmul_rn(xv, al);
-          s = __dadd_rn(s, __dmul_rn(v, xv));
-        }
-      }
-      if (G > 1) {
-#pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) s = __dadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
-      }
-      if (active && lane == 0) row_epilogue<MODE>(a, row, s, acc);
-      g0 += n;
     }
   }
   if (MODE == ROW_SPMV_DOT) {
@@ -688,138 +322,56 @@ __global__ void __launch_bounds__(THREADS) csr_stream_kernel(StreamArgs m, RowAr
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// warp-specialised streaming CSR kernel (the production hot kernel).
-//   warp NW          : producer -- one lane streams the CTA's val[]/col[] slice through the ring
-//                      with TMA bulk copies, re-filling a slot as soon as every consumer warp has
-//                      released it (empty[] mbarriers, count NW)
-//   warps 0 .. NW-1  : consumers -- each owns every NW-th step of 32/G consecutive rows, waits on the
-//                      full[] mbarriers of the chunks its row touches, walks the row in batches of U
-//                      entries (U independent x-gathers in flight per lane), applies the fused
-//                      epilogue, then releases the chunks it has moved past.
-// There is no block-wide barrier in the main loop: warps drift apart by up to the ring capacity,
-// so DRAM streaming, shared-memory reads and L1/L2 gathers of different warps overlap.
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+// CSR -> block-SELL conversion on the device: one lane per (slice, lane) position copies its block row
+// into the slice (coalesced writes; padding written as zero blocks with block column 0).
+// values_only: refresh of the values after gsb_mat_update_values (same sparsity).
+template <int BS>
+__global__ void __launch_bounds__(256) sell_fill_kernel(int64_t npos, int64_t n_brows, const int *__restrict__ perm,
+                                                        const int *__restrict__ slice_off, const int *__restrict__ rowptr,
+                                                        const int *__restrict__ col, const double *__restrict__ val,
+                                                        int *__restrict__ bcol, double *__restrict__ sval, int values_only) {
+  constexpr int BB = BS * BS;
+  const int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= npos) return;
+  const int64_t slice = pos >> 5;
+  const int lane = (int)(pos & 31);
+  const int64_t brow = perm ? (int64_t)perm[pos] : (pos < n_brows ? pos : -1);
+  const int so0 = slice_off[slice], width = slice_off[slice + 1] - so0;
+  int e0[BS] = {};
+  int nb = 0;
+  if (brow >= 0) {
+#pragma unroll
+    for (int i = 0; i < BS; ++i) e0[i] = rowptr[brow * BS + i];
+    nb = (rowptr[brow * BS + 1] - e0[0]) / BS;
+  }
+  int *cp = bcol + ((size_t)so0 << 5) + lane;
+  double *vp = sval + (((size_t)so0 * BB) << 5) + lane;
+  for (int k = 0; k < width; ++k) {
+    const bool in = k < nb;
+    if (!values_only) cp[(size_t)k * 32] = in ? col[e0[0] + k * BS] / BS : 0;
+#pragma unroll
+    for (int i = 0; i < BS; ++i)
+#pragma unroll
+      for (int j = 0; j < BS; ++j) vp[((size_t)k * BB + i * BS + j) * 32] = in ? val[e0[i] + k * BS + j] : 0.0;
+  }
 }
 
-template <int G, int MODE, int NW, int RING_LOG2, int CHUNK_LOG2, int U>
-__global__ void __launch_bounds__((NW + 1) * 32, 1) csr_stream_ws_kernel(StreamArgs m, RowArgs a) {
-  constexpr int THREADS = (NW + 1) * 32;
-  constexpr int RING = 1 << RING_LOG2;
-  constexpr int CHUNK = 1 << CHUNK_LOG2;
-  constexpr int NSLOT = RING / CHUNK;
-  constexpr int RW = 32 / G;  // rows per warp step
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  double *sval = reinterpret_cast<double *>(smem_raw);
-  int *scol = reinterpret_cast<int *>(smem_raw + (size_t)RING * 8);
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)RING * 12);
-  uint64_t *empty = full + NSLOT;
-  __shared__ double red_smem[(THREADS + 31) / 32];
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int R0 = m.cta_rows[blockIdx.x], R1 = m.cta_rows[blockIdx.x + 1];
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < NSLOT; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  double acc = 0.0;
-  if (R0 < R1) {
-    const int E0 = m.rowptr[R0], E1 = m.rowptr[R1];
-    const int S0 = E0 & ~3;  // 16-byte aligned start of this CTA's stream
-    const int nchunks = (E1 - S0 + CHUNK - 1) >> CHUNK_LOG2;
-    if (warp == NW) {
-      // ------------------------------------------------ producer
-      if (lane == 0) {
-        for (int c = 0; c < nchunks; ++c) {
-          const int slot = c & (NSLOT - 1);
-          if (c >= NSLOT) mbar_wait(&empty[slot], (uint32_t)(((c / NSLOT) - 1) & 1));
-          const int64_t start = (int64_t)S0 + ((int64_t)c << CHUNK_LOG2);
-          int64_t cnt = m.nnz_padded - start;
-          if (cnt > CHUNK) cnt = CHUNK;
-          mbar_expect_tx(&full[slot], (uint32_t)cnt * 12u);
-          tma_bulk_g2s(sval + (size_t)slot * CHUNK, m.val + start, (uint32_t)cnt * 8u, &full[slot]);
-          tma_bulk_g2s(scol + (size_t)slot * CHUNK, m.col + start, (uint32_t)cnt * 4u, &full[slot]);
-        }
-      }
-    } else {
-      // ------------------------------------------------ consumers
-      const int sub = lane / G, gl = lane % G;
-      int released = 0;  // meaningful in lane 0
-      int first = R0 + warp * RW;  // first row of this warp's current step
-      int row = first + sub;
-      int rp0 = 0, rp1 = 0;
-      if (row < R1) { rp0 = m.rowptr[row]; rp1 = m.rowptr[row + 1]; }
-      while (first < R1) {
-        const bool valid = row < R1;
-        RowPre<MODE> pre{};
-        if (valid && gl == 0) row_prefetch<MODE>(a, row, pre);
-        // row pointers of this warp's next step
-        const int nfirst = first + NW * RW, nrow = nfirst + sub;
-        int nrp0 = 0, nrp1 = 0;
-        if (nrow < R1) { nrp0 = m.rowptr[nrow]; nrp1 = m.rowptr[nrow + 1]; }
-        double s = 0.0;
-        if (valid) {
-          const int e0 = rp0, e1 = rp1;
-          if (e1 > e0) {
-            const int c0 = (e0 - S0) >> CHUNK_LOG2, c1 = (e1 - 1 - S0) >> CHUNK_LOG2;
-            for (int c = c0; c <= c1; ++c) mbar_wait(&full[c & (NSLOT - 1)], (uint32_t)((c / NSLOT) & 1));
-          }
-          if (gl == 0) s = row_init<MODE>(a, row);
-          const double al = a.alpha;
-          for (int k = e0 + gl; k < e1; k += U * G) {
-            int cc[U];
-            double vv[U], xv[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-              const int e = k + u * G;
-              const int p = (e - S0) & (RING - 1);
-              cc[u] = (e < e1) ? scol[p] : 0;
-              vv[u] = (e < e1) ? sval[p] : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) xv[u] = (k + u * G < e1) ? __ldg(a.x + cc[u]) : 0.0;
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-              if (k + u * G < e1) {
-                double t = xv[u];
-                if (MODE == ROW_SPMV) t = __dmul_rn(t, al);
-                s = __dadd_rn(s, __dmul_rn(vv[u], t));
-              }
-            }
-          }
-        }
-        if (G > 1) {
-#pragma unroll
-          for (int o = G / 2; o > 0; o >>= 1) s = __dadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
-        }
-        if (valid && gl == 0) row_epilogue_pre<MODE>(a, row, s, pre, acc);
-        // release the chunks this warp has moved past
-        const int e_next = __shfl_sync(0xffffffffu, (nfirst < R1) ? nrp0 : E1, 0);
-        const int pass = (nfirst < R1) ? ((e_next - S0) >> CHUNK_LOG2) : nchunks;
-        __syncwarp();
-        // (a chunk is released only once it has landed: a warp that skips a chunk must not arrive
-        //  on empty[] before the slot's previous use has been released by every warp, or its
-        //  arrival would be counted in the wrong phase)
-        if (lane == 0)
-          for (; released < pass; ++released) {
-            mbar_wait(&full[released & (NSLOT - 1)], (uint32_t)((released / NSLOT) & 1));
-            mbar_arrive(&empty[released & (NSLOT - 1)]);
-          }
-        first = nfirst; row = nrow; rp0 = nrp0; rp1 = nrp1;
-      }
-      if (lane == 0)
-        for (; released < nchunks; ++released) {
-          mbar_wait(&full[released & (NSLOT - 1)], (uint32_t)((released / NSLOT) & 1));
-          mbar_arrive(&empty[released & (NSLOT - 1)]);
-        }
-    }
-  }
-  if (MODE == ROW_SPMV_DOT) {
-    double v[1] = {acc};
-    grid_reduce_finish<THREADS, 1>(v, a.red, red_smem);
-  }
+// diag(A) of the own-own block (0 for a missing entry, like diag() of a Julia sparse matrix)
+__global__ void csr_diag_kernel(int64_t nrows, const int *__restrict__ rowptr, const int *__restrict__ col,
+                                const double *__restrict__ val, double *__restrict__ diag, int *__restrict__ diag_pos) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows) return;
+  double d = 0.0;
+  int pos = -1;
+  for (int e = rowptr[i]; e < rowptr[i + 1]; ++e)
+    if (col[e] == i) { d = val[e]; pos = e; }
+  diag[i] = d;
+  diag_pos[i] = pos;
+}
+__global__ void refresh_diag_kernel(int64_t nrows, const int *__restrict__ diag_pos, const double *__restrict__ val,
+                                    double *__restrict__ diag) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nrows) diag[i] = diag_pos[i] >= 0 ? val[diag_pos[i]] : 0.0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -908,6 +460,53 @@ __global__ void __launch_bounds__(THREADS) cg_update_kernel(int64_t n, ScalarRef
   grid_reduce_finish<THREADS, 1>(v, ro, red_smem);
 }
 
+// modified Gram-Schmidt, one launch per step (GMRESSolvers.jl:162-165): w -= h_prev * vprev (the axpy of
+// the previous step, h_prev read from its device slot) fused with the dot of the updated w against v
+// (v == nullptr: against itself -> the norm that closes the column).  Element-wise the same roundings
+// and the same grid-stride summation order as the separate ew_kernel / dot_kernel launches.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) mgs_step_kernel(int64_t n, double *__restrict__ w, const double *__restrict__ vprev,
+                                                           int slot_prev, const double *__restrict__ v, ReduceOut ro) {
+  __shared__ double red_smem[THREADS / 32];
+  const double b = vprev ? -ro.scal[slot_prev] : 0.0;
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * THREADS) {
+    double wi = w[i];
+    if (vprev) {
+      wi = __dadd_rn(__dmul_rn(1.0, wi), __dmul_rn(b, vprev[i]));
+      w[i] = wi;
+    }
+    acc = __dadd_rn(acc, __dmul_rn(wi, v ? v[i] : wi));
+  }
+  double r[1] = {acc};
+  grid_reduce_finish<THREADS, 1>(r, ro, red_smem);
+}
+
+// x += sum_i g_i z_i, applied vector after vector per element (the rounding sequence of the loop of
+// `x .+= g[i] .* Z[i]` broadcasts, GMRESSolvers.jl:193-196 / FGMRESSolvers.jl:191-193), one pass over x
+constexpr int MAXPY_MAX = 16;
+struct MultiAxpyArgs {
+  double *x;
+  const double *z[MAXPY_MAX];
+  double g[MAXPY_MAX];
+  int cnt;
+  int64_t n;
+};
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) multi_axpy_kernel(MultiAxpyArgs a) {
+  for (int64_t i = (int64_t)blockIdx.x * THREADS + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * THREADS) {
+    double xi = a.x[i];
+    double zv[MAXPY_MAX];
+#pragma unroll
+    for (int q = 0; q < MAXPY_MAX; ++q)
+      if (q < a.cnt) zv[q] = a.z[q][i];
+#pragma unroll
+    for (int q = 0; q < MAXPY_MAX; ++q)
+      if (q < a.cnt) xi = __dadd_rn(__dmul_rn(1.0, xi), __dmul_rn(a.g[q], zv[q]));
+    a.x[i] = xi;
+  }
+}
+
 // gather / scatter for halo exchange
 __global__ void pack_kernel(int64_t n, const int *__restrict__ ids, const double *__restrict__ v, double *__restrict__ buf) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) buf[i] = v[ids[i]];
@@ -991,15 +590,16 @@ __global__ void __launch_bounds__(256) p2p_wait_unpack_kernel(P2PWait w, double 
     v[w.rcv_ids[i]] = __ldcg(rcv_buf + i);
 }
 
-// diag extraction: invd[i] = 1/A[i,i]  (JacobiLinearSolvers.jl:20-23,29-34; own-own block)
-__global__ void inv_diag_kernel(int64_t nrows, const int *__restrict__ rowptr, const int *__restrict__ col,
-                                const double *__restrict__ val, double *__restrict__ invd) {
+// invd[i] = 1/A[i,i]  (JacobiLinearSolvers.jl:20-23,29-34; diagonal of the own-own block, kept per matrix)
+__global__ void inv_diag_kernel(int64_t nrows, const double *__restrict__ diag, double *__restrict__ invd) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nrows) return;
-  double d = 0.0;  // diag() of a sparse matrix returns 0 for a missing entry
-  for (int e = rowptr[i]; e < rowptr[i + 1]; ++e)
-    if (col[e] == i) d = val[e];
-  invd[i] = __ddiv_rn(1.0, d);
+  if (i < nrows) invd[i] = __ddiv_rn(1.0, diag[i]);
+}
+
+// assemble!: v[ids[i]] += buf[i] over one neighbour's segment (ids unique within a segment)
+__global__ void add_at_kernel(int64_t n, const int *__restrict__ ids, const double *__restrict__ buf, double *__restrict__ v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    v[ids[i]] = __dadd_rn(v[ids[i]], buf[i]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1019,64 +619,111 @@ __global__ void gj_set_identity_kernel(int64_t n, double *__restrict__ M) {  // 
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) M[i * 2 * n + n + i] = 1.0;
 }
-// one block: pivot = argmax_{i>=k} |M[i][k]|
-__global__ void gj_pivot_kernel(int64_t n, int64_t k, const double *__restrict__ M, int *__restrict__ piv,
-                                double *__restrict__ pivval) {
-  __shared__ double sv[256];
-  __shared__ int si[256];
-  double best = -1.0;
-  int bi = (int)k;
-  for (int64_t i = k + threadIdx.x; i < n; i += blockDim.x) {
-    const double v = fabs(M[i * 2 * n + k]);
-    if (v > best) { best = v; bi = (int)i; }
-  }
-  sv[threadIdx.x] = best;
-  si[threadIdx.x] = bi;
+
+// grid-wide barrier of a cooperative launch (all CTAs co-resident): monotone arrival counter
+__device__ __forceinline__ void grid_barrier(unsigned int *ctr, unsigned int &gen) {
   __syncthreads();
-  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-    if (threadIdx.x < o) {
-      if (sv[threadIdx.x + o] > sv[threadIdx.x] ||
-          (sv[threadIdx.x + o] == sv[threadIdx.x] && si[threadIdx.x + o] < si[threadIdx.x])) {
-        sv[threadIdx.x] = sv[threadIdx.x + o];
-        si[threadIdx.x] = si[threadIdx.x + o];
+  gen += 1;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    const unsigned int target = gen * gridDim.x;
+    for (;;) {
+      unsigned int cur;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cur) : "l"(ctr) : "memory");
+      if (cur >= target) break;
+    }
+  }
+  __syncthreads();
+}
+
+// Gauss-Jordan inverse with partial pivoting of the augmented matrix M = [A | I] (n x 2n, row-major), the
+// WHOLE elimination in ONE cooperative launch: per column (a) every CTA scans its rows for the pivot
+// candidate, (b) after a grid barrier every CTA reduces the candidates, one pass saves the scaled pivot row
+// and the elimination factors (taken before the row swap) and swaps, (c) after a second barrier all rows are
+// eliminated, third barrier.  Matrix reads use ld.global.cg: L1 is not coherent between SMs inside a launch.  Scratch: cand (2 doubles + 1 int per CTA), prow (2n), fcol (n).
+struct GJArgs {
+  int64_t n;
+  double *M;
+  double *prow, *fcol;
+  double *cand_abs, *cand_val;
+  int *cand_idx;
+  unsigned int *barrier;  // zero at launch
+};
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) gj_inverse_kernel(GJArgs g) {
+  __shared__ double sv[THREADS], sval[THREADS];
+  __shared__ int si[THREADS];
+  const int64_t n = g.n, ld = 2 * g.n;
+  unsigned int gen = 0;
+  for (int64_t k = 0; k < n; ++k) {
+    // (a) pivot candidates: argmax_{i>=k} |M[i][k]|, smallest index among equals
+    {
+      double best = -1.0, bval = 0.0;
+      int bi = (int)k;
+      for (int64_t i = k + (int64_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * THREADS) {
+        const double v = __ldcg(g.M + i * ld + k);
+        if (fabs(v) > best) { best = fabs(v); bi = (int)i; bval = v; }
+      }
+      sv[threadIdx.x] = best; si[threadIdx.x] = bi; sval[threadIdx.x] = bval;
+      __syncthreads();
+      for (int o = THREADS / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+          const int q = threadIdx.x + o;
+          if (sv[q] > sv[threadIdx.x] || (sv[q] == sv[threadIdx.x] && si[q] < si[threadIdx.x])) {
+            sv[threadIdx.x] = sv[q]; si[threadIdx.x] = si[q]; sval[threadIdx.x] = sval[q];
+          }
+        }
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) { g.cand_abs[blockIdx.x] = sv[0]; g.cand_idx[blockIdx.x] = si[0]; g.cand_val[blockIdx.x] = sval[0]; }
+    }
+    grid_barrier(g.barrier, gen);
+    // (b) every CTA reduces the candidates (same result everywhere)
+    {
+      double best = -1.0, bval = 0.0;
+      int bi = (int)k;
+      for (unsigned int q = threadIdx.x; q < gridDim.x; q += THREADS) {
+        const double v = __ldcg(g.cand_abs + q);
+        const int idx = __ldcg(g.cand_idx + q);
+        if (v > best || (v == best && idx < bi)) { best = v; bi = idx; bval = __ldcg(g.cand_val + q); }
+      }
+      sv[threadIdx.x] = best; si[threadIdx.x] = bi; sval[threadIdx.x] = bval;
+      __syncthreads();
+      for (int o = THREADS / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+          const int q = threadIdx.x + o;
+          if (sv[q] > sv[threadIdx.x] || (sv[q] == sv[threadIdx.x] && si[q] < si[threadIdx.x])) {
+            sv[threadIdx.x] = sv[q]; si[threadIdx.x] = si[q]; sval[threadIdx.x] = sval[q];
+          }
+        }
+        __syncthreads();
       }
     }
+    const int64_t p = si[0];
+    const double piv = sval[0];
     __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    *piv = si[0];
-    *pivval = M[(int64_t)si[0] * 2 * n + k];
-  }
-}
-// factors of the elimination step, taken BEFORE the row swap: fcol[i] = M[i][k], and the row
-// that will hold old row k after the swap (row piv) gets old M[k][k]
-__global__ void gj_fcol_kernel(int64_t n, int64_t k, const double *__restrict__ M, const int *__restrict__ piv,
-                               double *__restrict__ fcol) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int64_t p = *piv;
-  fcol[i] = (i == p) ? M[k * 2 * n + k] : M[i * 2 * n + k];
-}
-// prow = row piv / pivot ; row piv <- row k (row k itself is written by the eliminate kernel)
-__global__ void gj_swap_scale_kernel(int64_t n, int64_t k, double *__restrict__ M, const int *__restrict__ piv,
-                                     const double *__restrict__ pivval, double *__restrict__ prow) {
-  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= 2 * n) return;
-  const int64_t p = *piv;
-  const double a = M[p * 2 * n + j];
-  if (p != k) M[p * 2 * n + j] = M[k * 2 * n + j];
-  prow[j] = a / *pivval;
-}
-__global__ void gj_eliminate_kernel(int64_t n, int64_t k, double *__restrict__ M, const double *__restrict__ prow,
-                                    const double *__restrict__ fcol) {
-  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t i = blockIdx.y;
-  if (j >= 2 * n) return;
-  if (i == k) {
-    M[i * 2 * n + j] = prow[j];
-  } else {
-    const double f = fcol[i];
-    if (f != 0.0) M[i * 2 * n + j] -= f * prow[j];
+    // scaled pivot row, elimination factors (taken before the swap: row p will hold old row k), row swap
+    // row p <- row k.  Only row p is written here, and each element of it by the thread that read it.
+    for (int64_t t = (int64_t)blockIdx.x * THREADS + threadIdx.x; t < ld; t += (int64_t)gridDim.x * THREADS) {
+      if (t < n) g.fcol[t] = (t == p) ? __ldcg(g.M + k * ld + k) : __ldcg(g.M + t * ld + k);
+      const double a = __ldcg(g.M + p * ld + t);
+      if (p != k) g.M[p * ld + t] = __ldcg(g.M + k * ld + t);
+      g.prow[t] = a / piv;
+    }
+    grid_barrier(g.barrier, gen);
+    // (c) eliminate: row k <- prow, row i <- row i - fcol[i] * prow
+    for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
+      double *Mi = g.M + i * ld;
+      if (i == k) {
+        for (int64_t j = threadIdx.x; j < ld; j += THREADS) Mi[j] = __ldcg(g.prow + j);
+      } else {
+        const double f = __ldcg(g.fcol + i);
+        if (f != 0.0)
+          for (int64_t j = k + threadIdx.x; j < ld; j += THREADS) Mi[j] = __ldcg(Mi + j) - f * __ldcg(g.prow + j);
+      }
+    }
+    grid_barrier(g.barrier, gen);
   }
 }
 __global__ void gj_extract_kernel(int64_t n, int64_t row0, int64_t nrows, const double *__restrict__ M,

@@ -29,11 +29,6 @@ void spmv(gsb_mat_t A, gsb_vec_s &x, gsb_vec_s &y, double alpha, double beta);  
 void resid(gsb_mat_t A, gsb_vec_s &x, const gsb_vec_s &b, gsb_vec_s &out);             // out = b - A x
 void sweep(gsb_mat_t A, gsb_vec_s &dx_in, gsb_vec_s &r, const double *invd, double omega, gsb_vec_s &dx_out,
            gsb_vec_s &xacc);                                                            // fused Jacobi-Richardson sweep
-// niter fused sweeps r -= A dx ; dx' = omega*(invd.*r) ; x += dx' (the last one only updates r), S at a
-// time in one launch through the L2-pipelined kernel; dx_0 must be in dxa.  Returns false (and does
-// nothing) when the matrix is not eligible -- the caller then issues one launch per sweep.
-bool sweeps_pipelined(gsb_mat_t A, const double *invd, double omega, int niter, gsb_vec_s &r, gsb_vec_s &x,
-                      gsb_vec_s &dxa, gsb_vec_s &dxb);
 void spmv_dot(gsb_mat_t A, gsb_vec_s &x, gsb_vec_s &y, const gsb_vec_s &dotv, int slot); // y = A x ; scal[slot] = dotv.y
 void spmv_add(gsb_mat_t A, gsb_vec_s &x, gsb_vec_s &y, gsb_vec_s &xacc);                // y = A x ; xacc += y
 
@@ -45,6 +40,17 @@ void jacobi_dot(const double *invd, const gsb_vec_s &r, gsb_vec_s &z, int slot);
 void cg_update(ScalarRef alpha, const gsb_vec_s &p, const gsb_vec_s &w, gsb_vec_s &x, gsb_vec_s &r, int slot);
 // invd = 1 ./ diag(A_own_own)
 void inv_diag(gsb_mat_t A, double *invd);
+// matrix set-up helpers (device side of matrix.cu): diagonal + its CSR positions from the CSR arrays;
+// refresh of the diagonal from CSR-ordered values; CSR -> block-SELL conversion
+void csr_diag(gsb_mat_t A, const double *dval);
+void refresh_diag(gsb_mat_t A, const double *dval);
+void sell_fill(gsb_mat_t A, bool values_only, const double *dval);
+// modified Gram-Schmidt step: w -= scal[slot_prev]*vprev (vprev may be null) ; scal[slot] = w.v (v null: w.w)
+void mgs_step(gsb_vec_s &w, const gsb_vec_s *vprev, int slot_prev, const gsb_vec_s *v, int slot);
+// x += sum_i g[i]*z[i] (applied vector after vector per element)
+void multi_axpy(gsb_vec_s &x, const std::vector<const gsb_vec_s *> &z, const double *g);
+// assemble!(v): ghost -> owner accumulation through the reversed plan, then ghosts zeroed
+void assemble(gsb_vec_s &v, gsb_plan_t plan);
 
 // dense coarse solver pieces
 void dense_inverse_rows(gsb_mat_t A, DevBuf<double> &inv_rows, int64_t &n_global, int64_t &row_off);

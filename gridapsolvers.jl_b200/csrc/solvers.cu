@@ -7,28 +7,8 @@
 
 #include "ops.h"
 
-namespace gsb {
-int set_error(gsb_ctx_t ctx, const std::string &msg);
-}
+#include "api_macros.h"
 using namespace gsb;
-
-#define GSB_NULLCHK(h)                                         \
-  if (!(h)) {                                                 \
-    gsb::set_error(nullptr, "NULL handle passed to libgsb200"); \
-    return GSB_EINVAL;                                        \
-  }
-#define API_BEGIN try {
-#define API_END(ctx)                  \
-  }                                   \
-  catch (const gsb::Error &e) {       \
-    gsb::set_error((ctx), e.msg);     \
-    return e.code;                    \
-  }                                   \
-  catch (const std::exception &e) {   \
-    gsb::set_error((ctx), e.what());  \
-    return GSB_EINVAL;                \
-  }                                   \
-  return GSB_OK;
 
 namespace {
 
@@ -42,12 +22,23 @@ VecP make_vec(gsb_ctx_t ctx, int64_t n_own, int64_t n_ghost) {
   GSB_CUDA(cudaMemsetAsync(v->d, 0, sizeof(double) * std::max<int64_t>(1, n_own + n_ghost), ctx->stream));
   return v;
 }
+// device scalar slots owned by a solver: returned to the context's free list when the solver is destroyed
+struct Slots {
+  gsb_ctx_t ctx = nullptr;
+  int start = -1, n = 0;
+  void take(gsb_ctx_t c, int count) { ctx = c; n = count; start = c->alloc_slots(count); }
+  ~Slots() {
+    if (ctx && n > 0 && gsb::ctx_alive(ctx)) ctx->free_slots(start, n);
+  }
+};
+
 VecP domain_vec(gsb_mat_t A) { return make_vec(A->ctx, A->n_own_cols, A->n_ghost_cols); }  // allocate_in_domain
 VecP range_vec(gsb_mat_t A) { return make_vec(A->ctx, A->n_rows, 0); }                     // allocate_in_range
 
 void set_slot(gsb_ctx_t ctx, int slot, double v) {
-  ctx->h_scal[200] = v;  // pinned staging
-  GSB_CUDA(cudaMemcpyAsync(ctx->scal.p + slot, ctx->h_scal + 200, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  double *stage = ctx->h_scal + gsb_ctx_s::H_SCAL_READ;  // pinned staging word behind the read-back window
+  *stage = v;
+  GSB_CUDA(cudaMemcpyAsync(ctx->scal.p + slot, stage, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   GSB_CUDA(cudaStreamSynchronize(ctx->stream));
 }
 
@@ -63,6 +54,7 @@ void givens(double f, double g, double &cs, double &sn, double &r) {
 // ---------------------------------------------------------------- IdentitySolver
 struct IdentityNS : gsb_solver_s {
   const char *name() const override { return "Identity"; }
+  bool capturable() const override { return true; }
   void solve(Vec &x, Vec &b) override { vec_copy(x, b); }  // IdentityLinearSolvers.jl:23-26
 };
 
@@ -77,6 +69,7 @@ struct JacobiNS : gsb_solver_s {
     inv_diag(A, invd.p);  // JacobiLinearSolvers.jl:20-23,29-34
   }
   const char *name() const override { return "Jacobi"; }
+  bool capturable() const override { return true; }
   void update(gsb_mat_t A_) override { A = A_; inv_diag(A, invd.p); }    // :25-27,36-41
   void solve(Vec &x, Vec &b) override { ew_mul_raw(x, invd.p, b); }      // :43-56 own values only
 };
@@ -94,6 +87,7 @@ struct RichardsonNS : gsb_solver_s {
     Adx = domain_vec(A);
   }
   const char *name() const override { return "Richardson"; }
+  bool capturable() const override { return M->capturable(); }
   void update(gsb_mat_t A_) override { M->update(A_); A = A_; }  // :72-76
   // solve!(x,ns,r): updates x AND r in place (:84-98)
   void solve(Vec &x, Vec &r) override { apply(x, r, false); }
@@ -105,8 +99,6 @@ struct RichardsonNS : gsb_solver_s {
       if (niter <= 0) return;
       // iteration 1 prologue: dx = w*(invD*r) ; x += dx          (:91-93)
       jacobi_step(J->invd.p, r, omega, *dx, x, x_is_zero);
-      // large single-part levels: S sweeps per launch, matrix re-read from L2 (bit-identical result)
-      if (sweeps_pipelined(A, J->invd.p, omega, niter, r, x, *dx, *Adx)) return;
       for (int it = 1; it <= niter; ++it) {
         if (it < niter) {
           // r -= A dx  (:94-95) fused with the next iteration's dx = w*(invD*r) ; x += dx
@@ -136,6 +128,7 @@ struct FromSmootherNS : gsb_solver_s {
   VecP r;
   FromSmootherNS(gsb_mat_t A, gsb_solver_t s) : smoother(s) { ctx = A->ctx; r = domain_vec(A); }
   const char *name() const override { return "LinearSolverFromSmoother"; }
+  bool capturable() const override { return smoother->capturable(); }
   void update(gsb_mat_t A) override { smoother->update(A); }
   void solve(Vec &x, Vec &b) override {  // LinearSolverFromSmoothers.jl:44-50
     vec_copy(*r, b);
@@ -155,6 +148,7 @@ struct DenseLUNS : gsb_solver_s {
   int64_t n_global = 0, row_off = 0;
   explicit DenseLUNS(gsb_mat_t A_) : A(A_) { ctx = A->ctx; update(A_); }
   const char *name() const override { return "DenseLU"; }
+  bool capturable() const override { return true; }
   void update(gsb_mat_t A_) override {
     A = A_;
     dense_inverse_rows(A, inv_rows, n_global, row_off);
@@ -172,7 +166,9 @@ struct GMGNS : gsb_solver_s {
   VecP rh;  // finest level cache, GMGLinearSolvers.jl:391-396
   struct Work { VecP dxh, Adxh, dxH, rH, tP, tR; };
   std::vector<Work> work;  // :451-466
+  Slots slots;
   int slot_rr;
+  bool children_capturable = true, graph_failed = false;
   const char *name() const override { return "GMG"; }
   gsb_mat_t matrix() override { return mats[0]; }
   GMGNS(gsb_ctx_t c, int nlev_, const gsb_mat_t *m, const gsb_mat_t *ip, const gsb_mat_t *rs, const gsb_solver_t *pr,
@@ -189,7 +185,13 @@ struct GMGNS : gsb_solver_s {
     post.assign(po, po + nlev - 1);
     log.configure(maxiter, atol, rtol);
     has_log = true;
-    slot_rr = ctx->alloc_slots(2);
+    slots.take(ctx, 2);
+    slot_rr = slots.start;
+    // the preconditioner application may be replayed from a CUDA graph only if no child reads scalars back
+    // to the host or takes data-dependent host decisions (any LinearSolver is legal as smoother / coarsest
+    // solver, GMGLinearSolvers.jl:48-58; an inner Krylov solver is not capturable)
+    children_capturable = coarse->capturable();
+    for (int l = 0; l < nlev - 1; ++l) children_capturable = children_capturable && pre[(size_t)l]->capturable() && post[(size_t)l]->capturable();
     rh = domain_vec(mats[0]);
     work.resize((size_t)nlev - 1);
     for (int l = 0; l < nlev - 1; ++l) {
@@ -267,7 +269,7 @@ struct GMGNS : gsb_solver_s {
       // coarse-level kernels) is captured once into a CUDA graph and replayed
       // (multi-rank: NCCL collectives are capturable and the peer-memory halo exchange keeps its
       //  sequence number on the device, so the replay is valid there too; the two-stream overlap is not)
-      const bool use_graph = !ctx->profiling && ctx->opt("graph", "1") == "1" &&
+      const bool use_graph = !ctx->profiling && ctx->opt("graph", "1") == "1" && children_capturable && !graph_failed &&
                              (ctx->nranks == 1 || (!ctx->nccl_halo_in_use && ctx->opt("overlap", "0") != "1"));
       if (use_graph && graph_exec && graph_x == x.d && graph_b == b.d) {
         GSB_CUDA(cudaGraphLaunch(graph_exec, ctx->stream));
@@ -278,22 +280,32 @@ struct GMGNS : gsb_solver_s {
         if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
         const int64_t l0 = ctx->launches;
         cudaGraph_t g = nullptr;
-        GSB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-        try {
+        bool ok = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+          try {
+            dot(*rh, *rh, slot_rr);
+            cycle(cycle_type, 0, x, *rh);
+            dot(*rh, *rh, slot_rr + 1);
+          } catch (...) {
+            ok = false;
+          }
+          if (cudaStreamEndCapture(ctx->stream, &g) != cudaSuccess || g == nullptr) ok = false;
+          if (ok && cudaGraphInstantiate(&graph_exec, g, 0) != cudaSuccess) { ok = false; graph_exec = nullptr; }
+          if (g) cudaGraphDestroy(g);
+        }
+        if (ok) {
+          graph_launches = ctx->launches - l0;
+          graph_x = x.d; graph_b = b.d;
+          GSB_CUDA(cudaGraphLaunch(graph_exec, ctx->stream));
+        } else {
+          // something in the cycle could not be captured: clear the error state, never try again, run eagerly
+          (void)cudaGetLastError();
+          ctx->launches = l0;
+          graph_failed = true;
           dot(*rh, *rh, slot_rr);
           cycle(cycle_type, 0, x, *rh);
           dot(*rh, *rh, slot_rr + 1);
-        } catch (...) {
-          cudaStreamEndCapture(ctx->stream, &g);
-          if (g) cudaGraphDestroy(g);
-          throw;
         }
-        GSB_CUDA(cudaStreamEndCapture(ctx->stream, &g));
-        graph_launches = ctx->launches - l0;
-        GSB_CUDA(cudaGraphInstantiate(&graph_exec, g, 0));
-        GSB_CUDA(cudaGraphDestroy(g));
-        graph_x = x.d; graph_b = b.d;
-        GSB_CUDA(cudaGraphLaunch(graph_exec, ctx->stream));
       } else {
         dot(*rh, *rh, slot_rr);
         cycle(cycle_type, 0, x, *rh);
@@ -337,6 +349,7 @@ struct CGNS : gsb_solver_s {
   gsb_solver_t Pl;
   bool flexible;
   VecP w, p, z, r;  // CGSolvers.jl:42-48
+  Slots slots;
   int s_g0, s_pw, s_rr, s_delta;  // five consecutive slots: gamma[2], p.w, r.r, delta
   bool record = false;            // LanczosDiagnostic support: keep alpha_k, beta_k
   std::vector<double> alphas, betas;
@@ -347,7 +360,8 @@ struct CGNS : gsb_solver_s {
     log.configure(maxiter, atol, rtol);
     has_log = true;
     w = domain_vec(A); p = domain_vec(A); z = domain_vec(A); r = domain_vec(A);
-    s_g0 = ctx->alloc_slots(2); s_pw = ctx->alloc_slots(1); s_rr = ctx->alloc_slots(1); s_delta = ctx->alloc_slots(1);
+    slots.take(ctx, 5);
+    s_g0 = slots.start; s_pw = s_g0 + 2; s_rr = s_g0 + 3; s_delta = s_g0 + 4;
   }
   void update(gsb_mat_t A_) override {  // :57-63
     if (Pl) Pl->update(A_);
@@ -414,6 +428,7 @@ struct GMRESNS : gsb_solver_s {
   VecP zr, zl;
   std::vector<double> H, g, c, s;  // H column-major (ld = m+1)
   int ldH = 0;
+  Slots slots;
   int s_h, s_h_cap;
   const char *name() const override { return flex ? "FGMRES" : "GMRES"; }
   gsb_mat_t matrix() override { return A; }
@@ -431,7 +446,8 @@ struct GMRESNS : gsb_solver_s {
     zl = domain_vec(A);
     resize_host(m);
     s_h_cap = std::max(m, maxiter) + 4;
-    s_h = ctx->alloc_slots(s_h_cap);
+    slots.take(ctx, s_h_cap);
+    s_h = slots.start;
   }
   int mcur() const { return (int)V.size() - 1; }
   void resize_host(int m) {
@@ -456,10 +472,14 @@ struct GMRESNS : gsb_solver_s {
     if (Pl) Pl->update(A_);
     A = A_;
   }
+  void apply_Pr(Vec &out, Vec &x) {
+    ctx->hint_vec = x.d; ctx->hint_norm = 1.0;  // x = V[j], normalised just before
+    Pr->solve(out, x);
+    ctx->hint_vec = nullptr;  // only the solve it was meant for may consume the hint
+  }
   void krylov_mul(Vec &y, Vec &x, Vec *wr) {  // KrylovUtils.jl:17-32
-    if (Pr) { ctx->hint_vec = x.d; ctx->hint_norm = 1.0; }  // x = V[j], normalised just before
-    if (Pr && Pl) { Pr->solve(*wr, x); spmv(A, *wr, *zl, 1.0, 0.0); Pl->solve(y, *zl); }
-    else if (Pr) { Pr->solve(*wr, x); spmv(A, *wr, y, 1.0, 0.0); }
+    if (Pr && Pl) { apply_Pr(*wr, x); spmv(A, *wr, *zl, 1.0, 0.0); Pl->solve(y, *zl); }
+    else if (Pr) { apply_Pr(*wr, x); spmv(A, *wr, y, 1.0, 0.0); }
     else if (Pl) { spmv(A, x, *zl, 1.0, 0.0); Pl->solve(y, *zl); }
     else spmv(A, x, y, 1.0, 0.0);
   }
@@ -494,12 +514,19 @@ struct GMRESNS : gsb_solver_s {
         } else {
           krylov_mul(Vn, *V[(size_t)j - 1], zr.get());  // zr not re-zeroed, GMRESSolvers.jl:161
         }
-        // modified Gram-Schmidt (:162-165); coefficients stay on the device until the column is complete
-        for (int i = 0; i < j; ++i) {
-          dot(Vn, *V[(size_t)i], s_h + i);
-          ew_axpby(Vn, imm(1.0), Vn, slot_ratio(s_h + i, -1, 1), V[(size_t)i].get());
+        // modified Gram-Schmidt (:162-165), one launch per step: the axpy of step i-1 is fused with the dot
+        // of step i (same order, same roundings as the separate broadcasts); the coefficients stay on the
+        // device until the column is complete, the closing step also yields the norm of :166
+        if (ctx->opt("fuse_mgs", "1") == "1") {
+          for (int i = 0; i <= j; ++i)
+            mgs_step(Vn, i > 0 ? V[(size_t)i - 1].get() : nullptr, s_h + i - 1, i < j ? V[(size_t)i].get() : nullptr, s_h + i);
+        } else {
+          for (int i = 0; i < j; ++i) {
+            dot(Vn, *V[(size_t)i], s_h + i);
+            ew_axpby(Vn, imm(1.0), Vn, slot_ratio(s_h + i, -1, 1), V[(size_t)i].get());
+          }
+          dot(Vn, Vn, s_h + j);
         }
-        dot(Vn, Vn, s_h + j);
         std::vector<double> hcol((size_t)j + 1);
         ctx->read_scalars(s_h, j + 1, hcol.data());
         for (int i = 0; i < j; ++i) Hij(i, j - 1) = hcol[(size_t)i];
@@ -526,13 +553,19 @@ struct GMRESNS : gsb_solver_s {
         for (int k = i + 1; k < j; ++k) acc += Hij(i, k) * g[(size_t)k];
         g[(size_t)i] = (g[(size_t)i] - acc) / Hij(i, i);
       }
+      // solution update: x .+= g[i] .* Z[i] (FGMRES :191-193) / V[i] (:193-196), one pass over x for all i
+      auto basis = [&](std::vector<VecP> &B) {
+        std::vector<const Vec *> z;
+        for (int i = 0; i < j; ++i) z.push_back(B[(size_t)i].get());
+        return z;
+      };
       if (flex) {
-        for (int i = 0; i < j; ++i) ew_axpby(x, imm(1.0), x, imm(g[(size_t)i]), Z[(size_t)i].get());  // FGMRES :191-193
+        multi_axpy(x, basis(Z), g.data());
       } else if (!Pr) {
-        for (int i = 0; i < j; ++i) ew_axpby(x, imm(1.0), x, imm(g[(size_t)i]), V[(size_t)i].get());  // :193-196
+        multi_axpy(x, basis(V), g.data());
       } else {
         vec_fill(*zl, 0.0);
-        for (int i = 0; i < j; ++i) ew_axpby(*zl, imm(1.0), *zl, imm(g[(size_t)i]), V[(size_t)i].get());
+        multi_axpy(*zl, basis(V), g.data());
         Pr->solve(*zr, *zl);
         ew_axpby(x, imm(1.0), x, imm(1.0), zr.get());
       }
@@ -547,6 +580,7 @@ struct MINRESNS : gsb_solver_s {
   gsb_mat_t A;
   gsb_solver_t Pl;
   VecP Vs[3], Ws[3], Zs[3];  // MINRESSolvers.jl:39-44
+  Slots slots;
   int s0;
   const char *name() const override { return "MINRES"; }
   gsb_mat_t matrix() override { return A; }
@@ -555,7 +589,8 @@ struct MINRESNS : gsb_solver_s {
     log.configure(maxiter, atol, rtol);
     has_log = true;
     for (int i = 0; i < 3; ++i) { Vs[i] = domain_vec(A); Ws[i] = domain_vec(A); Zs[i] = domain_vec(A); }
-    s0 = ctx->alloc_slots(4);
+    slots.take(ctx, 4);
+    s0 = slots.start;
   }
   void update(gsb_mat_t A_) override {
     if (Pl) Pl->update(A_);
@@ -629,6 +664,11 @@ struct BlockNS : gsb_solver_s {
   std::vector<int64_t> off;
   std::vector<VecP> w, y;  // BlockTriangularSolvers.jl:135-143 (y zeroed at set-up only)
   const char *name() const override { return diagonal ? "BlockDiagonal" : "BlockTriangular"; }
+  bool capturable() const override {
+    for (gsb_solver_t c : solvers)
+      if (!c->capturable()) return false;
+    return true;
+  }
   BlockNS(gsb_ctx_t c, int nb_, const gsb_mat_t *b, const gsb_solver_t *s, const double *co, int half_, bool diag)
       : nb(nb_), half(half_), diagonal(diag) {
     ctx = c;
@@ -681,6 +721,7 @@ struct RichardsonLinearNS : gsb_solver_s {
   gsb_solver_t Pl;
   double omega;
   VecP z, r;  // RichardsonLinearSolvers.jl:33-40
+  Slots slots;
   int s_rr;
   const char *name() const override { return "RichardsonLinearSolver"; }
   gsb_mat_t matrix() override { return A; }
@@ -689,7 +730,8 @@ struct RichardsonLinearNS : gsb_solver_s {
     log.configure(maxiter, atol, rtol);
     has_log = true;
     z = domain_vec(A); r = domain_vec(A);
-    s_rr = ctx->alloc_slots(1);
+    slots.take(ctx, 1);
+    s_rr = slots.start;
   }
   void update(gsb_mat_t A_) override {
     if (Pl) Pl->update(A_);
@@ -725,6 +767,7 @@ struct SchurNS : gsb_solver_s {
   VecP du, bu, bp;  // SchurComplementSolvers.jl:40-45
   int64_t nu, np;
   const char *name() const override { return "SchurComplement"; }
+  bool capturable() const override { return A->capturable() && S->capturable(); }
   SchurNS(gsb_ctx_t c, gsb_solver_t A_, gsb_mat_t B_, gsb_mat_t C_, gsb_solver_t S_) : A(A_), S(S_), B(B_), C(C_) {
     ctx = c;
     GSB_CHECK(B->n_rows == C->n_own_cols && C->n_rows == B->n_own_cols, "Schur complement: B and C shapes do not match");
@@ -870,8 +913,7 @@ int gsb_solve(gsb_solver_t ns, gsb_vec_t x, gsb_vec_t b) {
   GSB_CUDA(cudaStreamSynchronize(ns->ctx->stream));
   API_END(ns->ctx)
 }
-int gsb_solve_host(gsb_solver_t ns, double *x_host, const double *b_host, int64_t n) {
-  GSB_NULLCHK(ns)
+static int solve_host_impl(gsb_solver_t ns, double *x_host, const double *b_host, int64_t n, bool x0_is_zero) {
   API_BEGIN
   gsb_ctx_t ctx = ns->ctx;
   // staging vectors sized like the caller's own values; ghost room is taken from the solver's
@@ -884,11 +926,20 @@ int gsb_solve_host(gsb_solver_t ns, double *x_host, const double *b_host, int64_
     st.b = make_vec(ctx, n, ng);
   }
   GSB_CUDA(cudaMemcpyAsync(st.b->d, b_host, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
-  GSB_CUDA(cudaMemcpyAsync(st.x->d, x_host, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  if (x0_is_zero) vec_fill(*st.x, 0.0);  // the caller vouches for x0 = 0: no upload of the initial guess
+  else GSB_CUDA(cudaMemcpyAsync(st.x->d, x_host, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
   ns->solve(*st.x, *st.b);
   GSB_CUDA(cudaMemcpyAsync(x_host, st.x->d, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
   GSB_CUDA(cudaStreamSynchronize(ctx->stream));
   API_END(ns->ctx)
+}
+int gsb_solve_host(gsb_solver_t ns, double *x_host, const double *b_host, int64_t n) {
+  GSB_NULLCHK(ns)
+  return solve_host_impl(ns, x_host, b_host, n, false);
+}
+int gsb_solve_host_zero_guess(gsb_solver_t ns, double *x_host, const double *b_host, int64_t n) {
+  GSB_NULLCHK(ns)
+  return solve_host_impl(ns, x_host, b_host, n, true);
 }
 int gsb_solver_log(gsb_solver_t ns, int *num_iters, double *residuals, int64_t cap, int *flag) {
   GSB_NULLCHK(ns)

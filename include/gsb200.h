@@ -63,23 +63,26 @@ int gsb_timer_stop(gsb_ctx_t ctx, float *ms);
 /* number of kernels this library has launched on this context so far */
 int gsb_launch_count(gsb_ctx_t ctx, int64_t *out);
 /* per-launch CUDA-event timing of the row kernels (SpMV / residual / sweep / transfer), aggregated
- * by (mode, kernel kind, rows, nnz); mode = 0 spmv, 1 residual, 2 fused sweep, 3 spmv+dot, 4 spmv+add */
+ * by (mode, kernel kind, rows, nnz); mode = 0 spmv, 1 residual, 2 fused sweep, 3 spmv+dot, 4 spmv+add;
+ * kernel kind = 0 CSR fallback kernel, 2 + 10*block_size (+100 when the rows are sorted) block-SELL-32 */
 int gsb_profile_start(gsb_ctx_t ctx);
 int gsb_profile_stop(gsb_ctx_t ctx, int cap, int *n_out, int *mode, int *stream_kernel, int64_t *nrows, int64_t *nnz,
                      int *count, double *total_ms);
-/* diagnostics (pure host): plan of the opt-in staged-x-window row kernel for a CSR matrix (int32, 0-based,
- * ascending columns): out[5] = {ok, chunks, segments, max window, total window}; lcol_check (nnz ints or NULL)
- * receives the column each entry would gather */
-int gsb_diag_xstage_plan(int64_t n_rows, const int *rowptr, const int *col, int chunk_rows, int gap, int cap,
-                         int64_t *out, int *lcol_check);
+/* diagnostics (pure host): the block-SELL-32 plan the library builds for a CSR matrix (int32, 0-based, ascending
+ * columns): out[8] = {ok, block size, sorted, block rows, slices, stored blocks incl. padding, blocks without
+ * padding, boundary slices}; pos_row / pos_len (n_slices*32 ints or NULL): block row (-1 = padding lane) and
+ * length in blocks of every (slice, lane) position.  sort_mode: -1 auto, 0 never, 1 always */
+int gsb_diag_sell_plan(int64_t n_rows, int64_t n_own_cols, int64_t n_ghost_cols, const int *rowptr, const int *col,
+                       int detect_blocks, int sort_mode, int64_t *out, int *pos_row, int *pos_len);
 /* diagnostics: average duration of `reps` back-to-back launches of one row-kernel mode on scratch vectors */
 int gsb_bench_rows(gsb_mat_t A, int mode, int reps, float *avg_ms);
 /* runtime knobs (also read from the environment variable GSB_OPTIONS="k=v,k=v" at gsb_init); for tests/tuning:
- *   spmv=auto|sell|stream|vector   row-kernel family          stream_kernel=ws|v1   TMA ring kernel flavour
+ *   spmv=auto|vector   row-kernel family (vector = CSR fallback kernel, only for matrices that keep their CSR arrays)
+ *   sell=1|0, block=1|0, sell_sort=auto|0|1   block-SELL-32 storage: on/off, DOF-block detection, row sorting (at matrix creation)
+ *   keep_csr=0|1, keep_csr_max_nnz=N          keep the CSR column ids / values on the device next to block-SELL
  *   graph=1|0      CUDA-graph replay of a maxiter=1 GMG      gmg_defer_log=1|0     device-resident GMG log norms
  *   p2p=1|0        NVLink peer-memory halo (at plan creation) overlap=0|1           two-stream halo overlap
- *   fuse_smoother=1|0  fused Jacobi-Richardson sweeps         pipe_stages=S         L2-pipelined multi-sweep kernel
- *   xstage=0|1     staged-x-window SELL kernel (at matrix creation), sell=1|0, *_min_rows thresholds */
+ *   fuse_smoother=1|0  fused Jacobi-Richardson sweeps         fuse_mgs=1|0          fused modified Gram-Schmidt steps */
 int gsb_set_option(gsb_ctx_t ctx, const char *key, const char *value);
 
 /* ---------------------------------------------------------------- exchange plan
@@ -110,6 +113,10 @@ int gsb_mat_create(gsb_ctx_t ctx, int64_t n_rows, int64_t n_own_cols, int64_t n_
 /* same sparsity, new values, in the order given at creation -- numerical_setup!(ns,A) support */
 int gsb_mat_update_values(gsb_mat_t A, const double *vals);
 int gsb_mat_info(gsb_mat_t A, int64_t *n_rows, int64_t *n_own_cols, int64_t *n_ghost_cols, int64_t *nnz);
+/* device storage the row kernels stream: kind 0 = CSR, 1 = block-SELL-32 (block_size x block_size DOF blocks, rows
+ * optionally sorted by length inside windows of 256); stored_entries includes padding; bytes_per_pass = bytes
+ * of matrix data one SpMV-type kernel reads (values + ids + per-row metadata).  Any out pointer may be NULL. */
+int gsb_mat_format(gsb_mat_t A, int *kind, int *block_size, int *sorted, int64_t *stored_entries, int64_t *bytes_per_pass);
 int gsb_mat_destroy(gsb_mat_t A);
 
 /* ---------------------------------------------------------------- PVector mirror */
@@ -128,6 +135,14 @@ int gsb_vec_fill(gsb_vec_t v, double value);  /* fill!(v,value) */
 int gsb_vec_copy(gsb_vec_t dst, gsb_vec_t src); /* copy!(dst,src): own values */
 /* consistent!(v) |> wait : owner -> ghost halo update through the plan */
 int gsb_vec_consistent(gsb_vec_t v, gsb_plan_t plan);
+/* assemble!(v) |> wait : ghost -> owner accumulation through the same plan reversed (contributions added
+ * neighbour after neighbour), ghost entries zeroed afterwards.  Call sites in the reference:
+ * LinearSolvers/SchwarzLinearSolvers.jl:44-49, MultilevelTools/GridTransferOperators.jl:425,544 */
+int gsb_vec_assemble(gsb_vec_t v, gsb_plan_t plan);
+/* page-lock / release a caller-owned host buffer (e.g. the storage of a Julia Vector{Float64}) so that
+ * gsb_solve_host / gsb_vec_set / gsb_vec_get run at pinned-memory speed */
+int gsb_host_register(gsb_ctx_t ctx, void *ptr, int64_t bytes);
+int gsb_host_unregister(gsb_ctx_t ctx, void *ptr);
 
 /* ---------------------------------------------------------------- array primitives */
 /* mul!(y,A,x,alpha,beta): y = beta*y + A*(alpha*x), halo of x included (3-arg mul! = alpha 1, beta 0) */
@@ -197,6 +212,9 @@ int gsb_solver_update(gsb_solver_t ns, gsb_mat_t A);
 int gsb_solve(gsb_solver_t ns, gsb_vec_t x, gsb_vec_t b);
 /* solve!(x,ns,b) with HOST own-value buffers: H2D of b and x0, solve, D2H of x (the e2e path) */
 int gsb_solve_host(gsb_solver_t ns, double *x_host, const double *b_host, int64_t n);
+/* same, the caller vouching for x0 = 0 (the usual `x = allocate_in_domain(A); fill!(x,0)` of the reference's
+ * drivers, test/LinearSolvers/GMGTests.jl:124-128): the initial guess is not uploaded */
+int gsb_solve_host_zero_guess(gsb_solver_t ns, double *x_host, const double *b_host, int64_t n);
 /* ConvergenceLog read-back (ConvergenceLogs.jl:42-49): num_iters, residuals[0..num_iters], flag */
 int gsb_solver_log(gsb_solver_t ns, int *num_iters, double *residuals, int64_t cap, int *flag);
 int gsb_solver_destroy(gsb_solver_t ns);

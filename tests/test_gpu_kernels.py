@@ -21,10 +21,35 @@ def _rand(n, seed):
     return np.random.default_rng(seed).standard_normal(n)
 
 
+KERNELS = ["vector", "sell", "sell_sorted"]
+
+
+def _select(ctx, kernel):
+    """row-kernel family for the matrices created next: CSR fallback kernel, block-SELL-32, block-SELL-32 with the
+    rows sorted by length inside windows of 256 (forced, even where the planner would not sort)"""
+    ctx.set_option("spmv", "vector" if kernel == "vector" else "auto")
+    ctx.set_option("sell_sort", "1" if kernel == "sell_sorted" else "auto")
+
+
+def _reset(ctx):
+    for k, v in (("spmv", "auto"), ("sell_sort", "auto"), ("block", "1"), ("keep_csr_max_nnz", "16777216"), ("fuse_smoother", "1")):
+        ctx.set_option(k, v)
+
+
+def _format(gsb, A):
+    import ctypes
+
+    kind, bs, srt = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    ent, byt = ctypes.c_int64(), ctypes.c_int64()
+    gsb._lib.check(gsb._lib.lib().gsb_mat_format(A.h, ctypes.byref(kind), ctypes.byref(bs), ctypes.byref(srt), ctypes.byref(ent),
+                                                 ctypes.byref(byt)))
+    return dict(kind=kind.value, bs=bs.value, sorted=bool(srt.value), entries=ent.value, bytes=byt.value)
+
+
 @pytest.mark.parametrize("nc", [(8, 8), (33, 17), (8, 8, 8), (20, 24, 16)])
-@pytest.mark.parametrize("kernel", ["vector", "stream", "sell"])
+@pytest.mark.parametrize("kernel", KERNELS)
 def test_spmv_bit_exact(gsb, ctx, nc, kernel):
-    ctx.set_option("spmv", kernel)
+    _select(ctx, kernel)
     try:
         sysm = fem.poisson(nc)
         A = dev_matrix(gsb, ctx, sysm.A)
@@ -42,20 +67,22 @@ def test_spmv_bit_exact(gsb, ctx, nc, kernel):
             yo = y0.copy()
             ola.mul5(yo, Ao, x, alpha, beta)
             assert np.array_equal(yd.get(), yo), (alpha, beta)
+        f = _format(gsb, A)
+        assert f["kind"] == 1 and f["sorted"] == (kernel == "sell_sorted")
     finally:
-        ctx.set_option("spmv", "auto")
+        _reset(ctx)
 
 
-@pytest.mark.parametrize("stream_kernel", ["ws", "v1"])
+@pytest.mark.parametrize("kernel", ["sell", "sell_sorted"])
 @pytest.mark.parametrize("nc", [(64, 64, 64), (96, 80, 72), (700, 600)])
-def test_stream_ring_wraparound_bit_exact(gsb, ctx, nc, stream_kernel):
-    """sizes at which every persistent CTA wraps its shared-memory ring several times and the
-    consumer warps drift apart: SpMV, residual and fused sweeps stay bit-identical to the oracle"""
+def test_sell_many_slices_bit_exact(gsb, ctx, nc, kernel):
+    """sizes with thousands of slices / sorting windows, matrices whose CSR arrays are released after the device-side
+    conversion: SpMV, residual and fused sweeps stay bit-identical to the oracle, run after run"""
     from gsb200 import synth
     from util import host_to_scipy
 
-    ctx.set_option("spmv", "stream")
-    ctx.set_option("stream_kernel", stream_kernel)
+    _select(ctx, kernel)
+    ctx.set_option("keep_csr_max_nnz", "1000")
     try:
         hh = synth.poisson_hierarchy_host(nc, 1)
         n = hh.levels[0].n_own
@@ -77,9 +104,79 @@ def test_stream_ring_wraparound_bit_exact(gsb, ctx, nc, stream_kernel):
         xo, ro = x0.copy(), r0.copy()
         OS.solve_(xo, OS.numerical_setup(OS.symbolic_setup(so, Ao), Ao), ro)
         assert np.array_equal(xd.get(), xo) and np.array_equal(rd.get(), ro)
+        # numerical_setup! on a matrix without CSR mirror: values and inverse diagonal are refreshed
+        A.update_values(3.0 * As.data)
+        gsb.numerical_setup_(ns, A)
+        gsb.mul_(yd, A, dev_vec(gsb, A, x))
+        ola.mul(yo, ola.CSR(3.0 * As), x)
+        assert np.array_equal(yd.get(), yo)
+        xd, rd = dev_vec(gsb, A, x0), dev_vec(gsb, A, r0)
+        gsb.solve_(xd, ns, rd)
+        Ao3 = ola.CSR(3.0 * As)
+        xo, ro = x0.copy(), r0.copy()
+        OS.solve_(xo, OS.numerical_setup(OS.symbolic_setup(so, Ao3), Ao3), ro)
+        assert np.array_equal(xd.get(), xo) and np.array_equal(rd.get(), ro)
     finally:
-        ctx.set_option("spmv", "auto")
-        ctx.set_option("stream_kernel", "ws")
+        _reset(ctx)
+
+
+@pytest.mark.parametrize("problem", ["elasticity_q2_3d", "stokes_velocity_q2_2d", "poisson_q2_3d"])
+@pytest.mark.parametrize("block", [1, 0])
+def test_block_sell_bit_exact(gsb, ctx, problem, block):
+    """long-row matrices (Q2 elements: 27..125-node stencils): 3x3 / 2x2 DOF blocks with one lane per block row and
+    rows sorted by length keep the sequential ascending-column order of every row => bit-identical to the oracle's
+    CSR loop for SpMV (3- and 5-argument), residual, fused Jacobi-Richardson sweeps and the transfer kernels"""
+    ctx.set_option("block", block)
+    try:
+        if problem == "elasticity_q2_3d":
+            H = fem.elasticity_hierarchy((6, 6, 6), 2, order=2)
+            bs = 3
+        elif problem == "stokes_velocity_q2_2d":
+            st = fem.stokes_cavity((24, 24), nlevels=2)
+            H = fem.Hierarchy([fem.AffineSystem(A=m, b=None, M=None, xstar=None, free=None, grid=None) for m in st["mats"]], st["P"], st["R"])
+            bs = 2
+        else:
+            H = fem.poisson_hierarchy((8, 8, 8), 2, order=2)
+            bs = 1
+        As = H.mats[0]
+        A, Ao = dev_matrix(gsb, ctx, As), ola.CSR(As)
+        f = _format(gsb, A)
+        assert f["kind"] == 1 and f["bs"] == (bs if block else 1) and f["sorted"]
+        assert f["entries"] <= 1.25 * As.nnz
+        n = As.shape[0]
+        x, y0 = _rand(n, 41), _rand(n, 42)
+        xd, yd = dev_vec(gsb, A, x), dev_vec(gsb, A, y0, domain=False)
+        gsb.mul_(yd, A, xd)
+        yo = np.zeros(n)
+        ola.mul(yo, Ao, x)
+        assert np.array_equal(yd.get(), yo)
+        for alpha, beta in [(-0.75, 1.0), (2.5, -0.5)]:
+            yd.set(y0)
+            gsb.mul_(yd, A, xd, alpha, beta)
+            yo = y0.copy()
+            ola.mul5(yo, Ao, x, alpha, beta)
+            assert np.array_equal(yd.get(), yo), (alpha, beta)
+        for niter in (1, 6):
+            s = gsb.RichardsonSmoother(gsb.JacobiLinearSolver(), niter, 2.0 / 3.0)
+            ns = gsb.numerical_setup(gsb.symbolic_setup(s, A), A)
+            x0, r0 = _rand(n, 43), _rand(n, 44)
+            xs, rs = dev_vec(gsb, A, x0), dev_vec(gsb, A, r0)
+            gsb.solve_(xs, ns, rs)
+            so = OS.RichardsonSmoother(OS.JacobiLinearSolver(), niter, 2.0 / 3.0)
+            xo, ro = x0.copy(), r0.copy()
+            OS.solve_(xo, OS.numerical_setup(OS.symbolic_setup(so, Ao), Ao), ro)
+            assert np.array_equal(xs.get(), xo) and np.array_equal(rs.get(), ro), niter
+        # transfers of the same hierarchy (prolongation rows of 1..27 entries, restriction rows up to 125)
+        for T in (H.P[0], H.R[0]):
+            Td, To = dev_matrix(gsb, ctx, T), ola.CSR(T)
+            xt = _rand(T.shape[1], 45)
+            xtd, ytd = dev_vec(gsb, Td, xt), dev_vec(gsb, Td, domain=False)
+            gsb.mul_(ytd, Td, xtd)
+            yt = np.zeros(T.shape[0])
+            ola.mul(yt, To, xt)
+            assert np.array_equal(ytd.get(), yt)
+    finally:
+        _reset(ctx)
 
 
 def test_spmv_csc_int64_one_based_upload(gsb, ctx):
@@ -125,10 +222,10 @@ def test_spmv_unsorted_rows_and_empty_rows(gsb, ctx):
     assert yd.get()[7] == 0.0
 
 
-@pytest.mark.parametrize("G_rows", [60, 200])  # average row length selects 4 / 16 lanes per row
-@pytest.mark.parametrize("kernel", ["vector", "stream", "sell"])
+@pytest.mark.parametrize("G_rows", [60, 200])  # average row length; the CSR fallback kernel uses 4 / 16 lanes per row
+@pytest.mark.parametrize("kernel", ["vector", "sell"])
 def test_spmv_long_rows(gsb, ctx, G_rows, kernel):
-    ctx.set_option("spmv", kernel)
+    _select(ctx, kernel)
     try:
         n = 4000
         A = sp.random(n, n, density=G_rows / n, random_state=11, format="csr")
@@ -139,10 +236,15 @@ def test_spmv_long_rows(gsb, ctx, G_rows, kernel):
         gsb.mul_(yd, Ad, xd)
         yo = np.zeros(n)
         ola.mul(yo, ola.CSR(A), x)
-        # several lanes per row => different summation tree: tolerance, not bit equality
-        assert np.allclose(yd.get(), yo, rtol=0, atol=1e-13 * np.abs(A).dot(np.abs(x)).max())
+        if kernel == "sell":
+            # random row lengths: sorted block-SELL, one lane per row => still the sequential order, bit for bit
+            assert _format(gsb, Ad)["kind"] == 1 and _format(gsb, Ad)["sorted"]
+            assert np.array_equal(yd.get(), yo)
+        else:
+            # several lanes per row => different summation tree: tolerance, not bit equality
+            assert np.allclose(yd.get(), yo, rtol=0, atol=1e-13 * np.abs(A).dot(np.abs(x)).max())
     finally:
-        ctx.set_option("spmv", "auto")
+        _reset(ctx)
 
 
 def test_blas1(gsb, ctx):
@@ -165,10 +267,10 @@ def test_blas1(gsb, ctx):
 
 
 @pytest.mark.parametrize("nc", [(16, 16), (12, 12, 12)])
-@pytest.mark.parametrize("kernel", ["vector", "stream", "sell"])
+@pytest.mark.parametrize("kernel", KERNELS)
 def test_richardson_jacobi_bit_exact(gsb, ctx, nc, kernel):
     """fused Jacobi-Richardson sweeps == reference statement sequence (RichardsonSmoothers.jl:84-98)"""
-    ctx.set_option("spmv", kernel)
+    _select(ctx, kernel)
     try:
         sysm = fem.poisson(nc)
         A = dev_matrix(gsb, ctx, sysm.A)
@@ -192,43 +294,7 @@ def test_richardson_jacobi_bit_exact(gsb, ctx, nc, kernel):
             ctx.set_option("fuse_smoother", "1")
             assert np.array_equal(xd2.get(), xo) and np.array_equal(rd2.get(), ro)
     finally:
-        ctx.set_option("spmv", "auto")
-        ctx.set_option("fuse_smoother", "1")
-
-
-@pytest.mark.parametrize("nc,force", [((20, 24, 16), True), ((33, 17), True), ((96, 96, 80), False)])
-@pytest.mark.parametrize("stages", [2, 3, 5, 10])
-def test_richardson_l2_pipelined_sweeps_bit_exact(gsb, ctx, nc, force, stages):
-    """S sweeps fused in one launch (inter-CTA dependency pipeline through L2) == the reference sequence, bit for bit"""
-    from gsb200 import synth
-    from util import host_to_scipy
-
-    ctx.set_option("pipe_stages", stages)
-    ctx.set_option("pipe_min_chunks", 1 if force else 2368)
-    try:
-        hh = synth.poisson_hierarchy_host(nc, 1)
-        n = hh.levels[0].n_own
-        As = host_to_scipy(hh.A[0], n)
-        A, Ao = dev_matrix(gsb, ctx, As), ola.CSR(As)
-        for niter in (10, 3):
-            s = gsb.RichardsonSmoother(gsb.JacobiLinearSolver(), niter, 2.0 / 3.0)
-            ns = gsb.numerical_setup(gsb.symbolic_setup(s, A), A)
-            x0, r0 = _rand(n, 31), _rand(n, 32)
-            xd, rd = dev_vec(gsb, A, x0), dev_vec(gsb, A, r0)
-            l0 = ctx.launch_count()
-            gsb.solve_(xd, ns, rd)
-            assert ctx.launch_count() - l0 == 1 + -(-niter // stages)  # prologue + ceil(niter/S) launches
-            so = OS.RichardsonSmoother(OS.JacobiLinearSolver(), niter, 2.0 / 3.0)
-            xo, ro = x0.copy(), r0.copy()
-            OS.solve_(xo, OS.numerical_setup(OS.symbolic_setup(so, Ao), Ao), ro)
-            assert np.array_equal(xd.get(), xo) and np.array_equal(rd.get(), ro)
-            # run to run reproducible
-            xd2, rd2 = dev_vec(gsb, A, x0), dev_vec(gsb, A, r0)
-            gsb.solve_(xd2, ns, rd2)
-            assert np.array_equal(xd2.get(), xo) and np.array_equal(rd2.get(), ro)
-    finally:
-        ctx.set_option("pipe_stages", 1)
-        ctx.set_option("pipe_min_chunks", 2368)
+        _reset(ctx)
 
 
 def test_linear_solver_from_smoother(gsb, ctx):

@@ -329,23 +329,89 @@ def test_bench_reference_arm_contract():
     assert d["value"] > 0 and d["dtype"] == "f64" and d["vs_baseline"] is None
 
 
-@pytest.mark.parametrize("nc", [(40, 40), (16, 16, 16), (24, 20, 12)])
-def test_xstage_plan_covers_every_column(nc):
-    """planner of the opt-in staged-x-window kernel (pure host): every entry's 16-bit window offset maps back to
-    its column; windows are small (a few stencil lines) and the total staged x traffic beats the per-entry gather"""
-    sysm = fem.poisson(nc)
-    A = sysm.A.tocsr()
+def _sell_plan(A, n_ghost=0, blocks=1, sort=-1):
+    A = sp.csr_matrix(A)
     A.sort_indices()
     rp, col = A.indptr.astype(np.int32), A.indices.astype(np.int32)
-    out = np.zeros(5, dtype=np.int64)
-    back = np.full(A.nnz, -7, dtype=np.int32)
-    L = gsb200._lib.lib()
-    rc = L.gsb_diag_xstage_plan(A.shape[0], rp.ctypes.data, col.ctypes.data, 256, 8, 6144, out.ctypes.data, back.ctypes.data)
-    assert rc == 0 and out[0] == 1
-    assert np.array_equal(back, col)
-    assert out[1] == -(-A.shape[0] // 256)
-    assert out[3] <= 6144
-    assert out[4] * 8 < 0.7 * A.nnz * 8  # staged window bytes < 70 % of the per-entry gather bytes
-    # a window cap that is too small is reported, not silently truncated
-    rc = L.gsb_diag_xstage_plan(A.shape[0], rp.ctypes.data, col.ctypes.data, 256, 8, 64, out.ctypes.data, None)
-    assert rc == 0 and out[0] == 0
+    out = np.zeros(8, dtype=np.int64)
+    nsl = -(-A.shape[0] // 32)
+    prow, plen = np.full(nsl * 32, -9, dtype=np.int32), np.zeros(nsl * 32, dtype=np.int32)
+    rc = gsb200._lib.lib().gsb_diag_sell_plan(A.shape[0], A.shape[1] - n_ghost, n_ghost, rp.ctypes.data, col.ctypes.data, blocks, sort,
+                                              out.ctypes.data, prow.ctypes.data, plen.ctypes.data)
+    assert rc == 0
+    keys = ("ok", "bs", "sorted", "n_brows", "n_slices", "blocks", "sum_blocks", "bnd_slices")
+    d = dict(zip(keys, (int(v) for v in out)))
+    ns = d["n_slices"] * 32
+    return d, prow[:ns], plen[:ns], rp
+
+
+def test_sell_plan_scalar_q1_is_unsorted_and_tight():
+    """Q1 Poisson: rows of one mesh line have the same length => no sorting, < 3 % padding, block size 1"""
+    d, prow, plen, rp = _sell_plan(fem.poisson((24, 20, 12)).A)
+    assert d["ok"] and d["bs"] == 1 and not d["sorted"]
+    assert d["blocks"] <= 1.06 * d["sum_blocks"]
+    n = d["n_brows"]
+    assert np.array_equal(prow[:n], np.arange(n)) and (prow[n:] == -1).all()
+    assert np.array_equal(plen[:n], np.diff(rp))
+
+
+def test_sell_plan_q2_elasticity_detects_3x3_blocks_and_sorts_rows():
+    """Q2 vector-valued elasticity (C4): node-major dofs => aligned 3x3 blocks; 125/75/45/27-node stencils alternate
+    along a mesh line => rows are sorted by length inside windows of 256 block rows, which brings the padding of
+    the 32-row slices from ~25 % down to a few %; the permutation is a bijection that stays inside its window"""
+    sysm = fem.elasticity((6, 6, 6), order=2)
+    A = sysm.A
+    d, prow, plen, rp = _sell_plan(A)
+    assert d["ok"] and d["bs"] == 3 and d["sorted"]
+    nb = A.shape[0] // 3
+    assert d["n_brows"] == nb and d["sum_blocks"] * 9 == A.nnz
+    assert d["blocks"] <= 1.12 * d["sum_blocks"]
+    d0, _, _, _ = _sell_plan(A, sort=0)
+    assert d0["bs"] == 3 and not d0["sorted"] and d0["blocks"] > 1.15 * d0["sum_blocks"]
+    real = prow[prow >= 0]
+    assert np.array_equal(np.sort(real), np.arange(nb))
+    pos = np.flatnonzero(prow >= 0)
+    assert (pos // 256 == real // 256).all()
+    assert np.array_equal(plen[pos], np.diff(rp)[real * 3] // 3)
+    for w in range(0, len(prow), 256):  # descending inside every window
+        assert (np.diff(plen[w:w + 256]) <= 0).all()
+    # block detection can be switched off: same matrix as scalar rows
+    d1, _, _, _ = _sell_plan(A, blocks=0)
+    assert d1["bs"] == 1 and d1["sum_blocks"] == A.nnz
+
+
+def test_sell_plan_rejects_false_block_structure():
+    """a matrix whose size is a multiple of 3 but whose sparsity is not made of aligned 3x3 blocks keeps block size 1;
+    2-component vector problems (Stokes velocity block) get 2x2 blocks"""
+    d, _, _, _ = _sell_plan(fem.poisson((10, 10)).A)  # 81 rows
+    assert d["bs"] == 1
+    st = fem.stokes_cavity((8, 8))
+    d, _, _, _ = _sell_plan(st["A"])
+    assert d["ok"] and d["bs"] == 2
+    # one entry removed from one row of a block row breaks the structure
+    A = fem.elasticity((2, 2, 2), order=2).A.tolil()
+    A[4, A.rows[4][0]] = 0
+    A = sp.csr_matrix(A)
+    A.eliminate_zeros()
+    d, _, _, _ = _sell_plan(A)
+    assert d["bs"] == 1
+
+
+def test_sell_plan_boundary_slices_follow_ghost_columns():
+    lp = synth.make_level_part((16, 8, 8), (2, 1, 1), 0)
+    rp, col, val, b = synth.poisson_rows(lp)
+    A = synth.to_scipy(rp, col, val, lp.n_own + lp.n_ghost)
+    d, prow, plen, _ = _sell_plan(A, n_ghost=lp.n_ghost)
+    has_ghost = np.array([col[rp[i + 1] - 1] >= lp.n_own for i in range(lp.n_own)])
+    expect = {int(i) // 32 for i in np.flatnonzero(has_ghost)} if not d["sorted"] else None
+    assert d["ok"] and d["bnd_slices"] > 0
+    if expect is not None:
+        assert d["bnd_slices"] == len(expect)
+
+
+def test_sell_plan_prolongation_short_rows():
+    """prolongations have 1/2/4/8 entries per row: sorting keeps the padding small"""
+    H = fem.poisson_hierarchy((16, 16, 16), 2)
+    d, _, _, _ = _sell_plan(H.P[0])
+    assert d["ok"] and d["bs"] == 1
+    assert d["blocks"] <= 1.6 * d["sum_blocks"]

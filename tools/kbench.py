@@ -1,5 +1,7 @@
-"""Row-kernel micro-benchmark: achieved algorithmic GB/s of every row-kernel mode on the fine-level
-Poisson matrices (C2: 128^3, C3 unit: 256^3).  usage: python tools/kbench.py [cells ...] [--opt k=v ...]"""
+"""Row-kernel micro-benchmark: achieved GB/s of every row-kernel mode on the fine-level matrices of the
+BASELINE configs.  usage: python tools/kbench.py [poisson:CELLS | elasticity:CELLS | stokes:CELLS ...] [k=v options]
+Reports, per mode: time, ALGORITHMIC GB/s (12 B per non-zero + per-row vector traffic) and the GB/s
+of the bytes the block-SELL format actually stores (8 + 4/bs^2 B per stored entry incl. padding)."""
 import json
 import os
 import sys
@@ -11,24 +13,48 @@ from gsb200 import synth
 PER_ROW = {"spmv": 20, "spmv_dot": 28, "residual": 28, "sweep": 44, "spmv_add": 36}
 
 
+def peak():
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
 def main():
-    cells = [int(a) for a in sys.argv[1:] if a.isdigit()] or [128]
-    opts = [a.split("=", 1) for a in sys.argv[1:] if "=" in a and not a.startswith("--")]
+    specs = [a for a in sys.argv[1:] if ":" in a] or ["poisson:128"]
+    opts = [a.split("=", 1) for a in sys.argv[1:] if "=" in a and ":" not in a]
     ctx = gsb.Context()
     for k, v in opts:
         ctx.set_option(k, v)
-    peak = 6545.3
-    for c in cells:
-        lp = synth.make_level_part((c,) * 3, (1, 1, 1), 0)
-        rp, col, val, b = synth.poisson_rows(lp)
-        A = gsb.SparseMatrix(ctx, lp.n_own, lp.n_own, 0, rp, col, val)
+    pk = peak()
+    for spec in specs:
+        kind, c = spec.split(":")
+        c = int(c)
+        if kind == "poisson":
+            lp = synth.make_level_part((c,) * 3, (1, 1, 1), 0)
+            rp, col, val, b = synth.poisson_rows(lp)
+            n = lp.n_own
+        elif kind == "elasticity":
+            rp, col, val, b, n = synth.elasticity_rows((c,) * 3)
+        elif kind == "stokes":
+            st = synth.stokes_cavity_host((c, c), nlevels=1)
+            rp, col, val = st["A"]
+            n = rp.shape[0] - 1
+        else:
+            raise SystemExit("unknown problem " + kind)
+        A = gsb.SparseMatrix(ctx, n, n, 0, rp, col, val)
         nnz = int(rp[-1])
-        out = {"cells": c, "rows": lp.n_own, "nnz": nnz, "opts": dict(opts)}
+        fmt = A.format()
+        out = {"problem": spec, "rows": n, "nnz": nnz, "format": fmt, "opts": dict(opts)}
         for mode in ("spmv", "residual", "sweep", "spmv_dot"):
             ms = A.bench_rows(mode, 30)
-            gbs = (12 * nnz + PER_ROW[mode] * lp.n_own) / (ms * 1e-3) / 1e9
-            out[mode] = {"us": round(ms * 1e3, 1), "GBps": round(gbs, 0), "frac": round(gbs / peak, 3)}
+            gbs = (12 * nnz + PER_ROW[mode] * n) / (ms * 1e-3) / 1e9
+            fgbs = (fmt["bytes_per_pass"] + PER_ROW[mode] * n - 4 * n) / (ms * 1e-3) / 1e9
+            out[mode] = {"us": round(ms * 1e3, 1), "GBps_algorithmic": round(gbs, 0), "frac": round(gbs / pk, 3),
+                         "GBps_format_bytes": round(fgbs, 0), "frac_format": round(fgbs / pk, 3)}
         print(json.dumps(out), flush=True)
+        del A
 
 
 if __name__ == "__main__":
