@@ -163,7 +163,8 @@ def synth():
         tr = [c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p]
         S.synth_prolong_rows.argtypes = tr
         S.synth_restrict_rows.argtypes = tr
-        for f in (S.synth_poisson_rows, S.synth_mass_rows, S.synth_prolong_rows, S.synth_restrict_rows):
+        S.synth_fe_rows.argtypes = [c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_i64, c_p, c_p, c_i, c_p, c_p, c_p, c_p]
+        for f in (S.synth_poisson_rows, S.synth_mass_rows, S.synth_prolong_rows, S.synth_restrict_rows, S.synth_fe_rows):
             f.restype = None
         _synth = S
     return _synth

@@ -410,11 +410,8 @@ static void launch_sell_inst(gsb_ctx_t ctx, const SellArgs &m, const RowArgs &a,
     switch (variant) {
       case 1: GSB_SELL(9, 3); break;
       case 2: GSB_SELL(14, 2); break;
-      default:
-        // the fused-dot mode prefers the 70-register schedule (its block reduction keeps fewer CTAs busy at the tail)
-        if (MODE == ROW_SPMV_DOT) GSB_SELL(9, 1);
-        else GSB_SELL(9, 4);
-        break;
+      case 3: GSB_SELL(9, 1); break;
+      default: GSB_SELL(9, 4); break;
     }
   } else if constexpr (BS == 2) {
     switch (variant) {

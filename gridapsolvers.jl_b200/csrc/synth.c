@@ -227,3 +227,116 @@ void synth_restrict_rows(int d, const int64_t *olo, const int64_t *ohi, const in
     }
   }
 }
+
+/* -------------------------------------------------------------------------------------------
+ * Generic tensor-product Lagrange generator (Q_p, p = order, ncomp components per node, node-major
+ * dofs) on a uniform Cartesian mesh: rows of the assembled matrix for the free nodes, computed row by
+ * row from ONE element matrix Ke (all cells are congruent) -- the full-size C4 system (64^3 Q2 cells,
+ * 1.24e9 non-zeros) is generated in parallel without any COO intermediate.  Plays the role of the
+ * Gridap assembly of test/Applications/Elasticity.jl:31-37 (C4) and of the velocity block of
+ * joss_paper/demo.jl:20-91 (C5); tests/ check it against the oracle's element-by-element assembly.
+ *
+ *   Ke        : (nb*ncomp)^2 row-major, local dof = a*ncomp + c, local node a lexicographic (x fastest)
+ *   Fe        : nb*ncomp element load vector or NULL
+ *   node_free : per node of the (order*ncell+1)^d node grid (x fastest): index among the free nodes or -1
+ *   free_nodes: node id of every free node (ascending)
+ *   ud        : Dirichlet values per (node, comp) or NULL; b (n_free*ncomp) receives Fe sums - K_ij ud_j
+ * pass 0: rowptr[r+1] = entries of row r (caller prefix-sums); pass 1: fill col/val (ascending columns) and b. */
+void synth_fe_rows(int d, int order, int ncomp, const int64_t *ncell, const double *Ke, const double *Fe,
+                   const int32_t *node_free, int64_t n_free_nodes, const int64_t *free_nodes, const double *ud, int pass,
+                   int64_t *rowptr, int32_t *col, double *val, double *b) {
+  int64_t nn[MAXD] = {1, 1, 1};
+  for (int k = 0; k < d; ++k) nn[k] = (int64_t)order * ncell[k] + 1;
+  const int p1 = order + 1, w = 2 * order + 1;
+  int nb = 1, nslot = 1;
+  for (int k = 0; k < d; ++k) { nb *= p1; nslot *= w; }
+  const int nv = nb * ncomp;
+#pragma omp parallel
+  {
+    double *S = (double *)malloc(sizeof(double) * (size_t)ncomp * nslot * ncomp);
+    unsigned char *touched = (unsigned char *)malloc((size_t)nslot);
+    int64_t *slot_node = (int64_t *)malloc(sizeof(int64_t) * (size_t)nslot);
+#pragma omp for schedule(static)
+    for (int64_t fn = 0; fn < n_free_nodes; ++fn) {
+      const int64_t nid = free_nodes[fn];
+      int64_t g[MAXD] = {0, 0, 0};
+      g[0] = nid % nn[0];
+      if (d > 1) g[1] = (nid / nn[0]) % nn[1];
+      if (d > 2) g[2] = nid / (nn[0] * nn[1]);
+      memset(touched, 0, (size_t)nslot);
+      if (pass) memset(S, 0, sizeof(double) * (size_t)ncomp * nslot * ncomp);
+      double fsum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      /* cells containing the node, per direction: (cell index, local node index) */
+      int64_t cc[MAXD][2];
+      int ca[MAXD][2], cn[MAXD] = {1, 1, 1};
+      for (int k = 0; k < d; ++k) {
+        if (g[k] % order == 0) {
+          const int64_t c1 = g[k] / order;
+          cn[k] = 0;
+          if (c1 - 1 >= 0) { cc[k][cn[k]] = c1 - 1; ca[k][cn[k]] = order; cn[k]++; }
+          if (c1 < ncell[k]) { cc[k][cn[k]] = c1; ca[k][cn[k]] = 0; cn[k]++; }
+        } else {
+          cn[k] = 1; cc[k][0] = g[k] / order; ca[k][0] = (int)(g[k] % order);
+        }
+      }
+      for (int iz = 0; iz < (d > 2 ? cn[2] : 1); ++iz)
+        for (int iy = 0; iy < (d > 1 ? cn[1] : 1); ++iy)
+          for (int ix = 0; ix < cn[0]; ++ix) {
+            const int sel[MAXD] = {ix, iy, iz};
+            int a = 0, stride = 1;
+            for (int k = 0; k < d; ++k) { a += ca[k][sel[k]] * stride; stride *= p1; }
+            if (pass && Fe)
+              for (int c = 0; c < ncomp; ++c) fsum[c] += Fe[a * ncomp + c];
+            for (int bn = 0; bn < nb; ++bn) {
+              int rem = bn, slot = 0, sstride = 1;
+              for (int k = 0; k < d; ++k) {
+                const int bk = rem % p1;
+                rem /= p1;
+                const int64_t o = cc[k][sel[k]] * order + bk - g[k];  /* in [-order, order] */
+                slot += (int)(o + order) * sstride;
+                sstride *= w;
+              }
+              touched[slot] = 1;
+              if (pass)
+                for (int c = 0; c < ncomp; ++c)
+                  for (int c2 = 0; c2 < ncomp; ++c2)
+                    S[((size_t)c * nslot + slot) * ncomp + c2] += Ke[(size_t)(a * ncomp + c) * nv + bn * ncomp + c2];
+            }
+          }
+      /* neighbour node of every touched slot */
+      int cnt = 0;
+      for (int slot = 0; slot < nslot; ++slot) {
+        if (!touched[slot]) continue;
+        int rem = slot;
+        int64_t q = 0, qstride = 1;
+        for (int k = 0; k < d; ++k) {
+          const int64_t o = rem % w - order;
+          rem /= w;
+          q += (g[k] + o) * qstride;
+          qstride *= nn[k];
+        }
+        slot_node[slot] = q;
+        if (node_free[q] >= 0) cnt += ncomp;
+      }
+      for (int c = 0; c < ncomp; ++c) {
+        const int64_t row = fn * ncomp + c;
+        if (pass == 0) { rowptr[row + 1] = cnt; continue; }
+        int64_t e = rowptr[row];
+        double bi = fsum[c];
+        for (int slot = 0; slot < nslot; ++slot) {
+          if (!touched[slot]) continue;
+          const int64_t q = slot_node[slot];
+          const int32_t fq = node_free[q];
+          const double *Sr = S + ((size_t)c * nslot + slot) * ncomp;
+          if (fq >= 0) {
+            for (int c2 = 0; c2 < ncomp; ++c2) { col[e] = fq * ncomp + c2; val[e] = Sr[c2]; ++e; }
+          } else if (ud) {
+            for (int c2 = 0; c2 < ncomp; ++c2) bi -= Sr[c2] * ud[q * ncomp + c2];
+          }
+        }
+        if (b) b[row] = bi;
+      }
+    }
+    free(S); free(touched); free(slot_node);
+  }
+}

@@ -299,3 +299,271 @@ def upload_hierarchy(ctx, hh: HostHierarchy) -> DeviceHierarchy:
         Ps.append(SparseMatrix(ctx, f.n_own, co.n_own, co.n_ghost, rp, c, v, plan=plans[l + 1]))
         Rs.append(SparseMatrix(ctx, co.n_own, f.n_own, f.n_ghost, rr, rc, rv, plan=plans[l]))
     return DeviceHierarchy(ctx, hh, plans, As, Ps, Rs)
+
+
+# ------------------------------------------------------------------------------------------------
+# Q_p tensor-product Lagrange problems on uniform Cartesian meshes (C4: 3D Q2 vector-valued elasticity,
+# C5: 2D Q2-P1disc Stokes).  The element matrices are computed here (numpy), the assembled rows by the
+# generic C generator synth_fe_rows (one element matrix, all cells congruent) -- no COO intermediate, so
+# the full-size C4 system (64^3 cells, 6.4 M dofs, 1.24e9 non-zeros) is generated in seconds.
+# Numbering: nodes lexicographic over the (p*n+1)^d node grid (x fastest), node-major vector dofs, free
+# dofs = non-Dirichlet nodes in lexicographic order (for Q2 a permutation of Gridap's vertex/edge/face/
+# interior numbering).  tests/ cross-check these generators against the oracle's own
+# element-by-element assembly (oracle/fem.py).
+
+
+def _gauss01(npts):
+    x, w = np.polynomial.legendre.leggauss(npts)
+    return 0.5 * (x + 1.0), 0.5 * w
+
+
+def _lagrange_1d(order, xi):
+    """values N[q,a] and derivatives dN[q,a] of the equispaced Lagrange basis of degree `order` on [0,1]"""
+    nodes = np.linspace(0.0, 1.0, order + 1)
+    xi = np.asarray(xi, dtype=np.float64)
+    N = np.ones((xi.shape[0], order + 1))
+    dN = np.zeros((xi.shape[0], order + 1))
+    for a in range(order + 1):
+        others = [b for b in range(order + 1) if b != a]
+        den = np.prod([nodes[a] - nodes[b] for b in others])
+        N[:, a] = np.prod([xi - nodes[b] for b in others], axis=0) / den
+        for c in others:
+            dN[:, a] += np.prod([xi - nodes[b] for b in others if b != c], axis=0) / den if len(others) > 1 else 1.0 / den
+    return N, dN
+
+
+def _tensor_basis(order, d, h, nq):
+    """phi[q,a], grad[q,a,dim], w[q] of the Q_order basis on a cell of size h; q and a lexicographic, x fastest"""
+    xi, wq = _gauss01(nq)
+    N1, dN1 = _lagrange_1d(order, xi)
+    p1 = order + 1
+    qi = np.stack(np.meshgrid(*[np.arange(nq)] * d, indexing="ij"), axis=-1).reshape(-1, d)[:, ::-1]  # x fastest
+    ai = np.stack(np.meshgrid(*[np.arange(p1)] * d, indexing="ij"), axis=-1).reshape(-1, d)[:, ::-1]
+    # reorder so that the FIRST listed index varies fastest: build explicit lexicographic (x fastest) lists
+    qi = np.array([[(Q // nq**k) % nq for k in range(d)] for Q in range(nq**d)])
+    ai = np.array([[(A // p1**k) % p1 for k in range(d)] for A in range(p1**d)])
+    w = np.ones(nq**d)
+    for k in range(d):
+        w *= wq[qi[:, k]] * h[k]
+    phi = np.ones((nq**d, p1**d))
+    grad = np.ones((nq**d, p1**d, d))
+    for k in range(d):
+        Nk = N1[qi[:, k]][:, ai[:, k]]
+        dNk = dN1[qi[:, k]][:, ai[:, k]] / h[k]
+        phi *= Nk
+        for g in range(d):
+            grad[:, :, g] *= dNk if g == k else Nk
+    return phi, grad, w
+
+
+def _node_grid(ncell, order):
+    nn = tuple(order * n + 1 for n in ncell)
+    grids = np.meshgrid(*[np.arange(n) for n in nn], indexing="ij")
+    mi = np.stack([g.ravel(order="F") for g in grids], axis=1)  # (nnodes, d), x fastest
+    return nn, mi
+
+
+def fe_rows(ncell, order, ncomp, Ke, dirichlet_nodes, Fe=None, ud=None):
+    """assembled rows (rowptr, col int32, val, b, n_free_dofs, free_node_ids) of the free dofs"""
+    S = _lib.synth()
+    d = len(ncell)
+    nc = np.array(ncell, dtype=np.int64)
+    free_nodes = np.flatnonzero(~dirichlet_nodes).astype(np.int64)
+    node_free = np.full(dirichlet_nodes.shape[0], -1, dtype=np.int32)
+    node_free[free_nodes] = np.arange(free_nodes.shape[0], dtype=np.int32)
+    n = free_nodes.shape[0] * ncomp
+    Ke = np.ascontiguousarray(Ke, dtype=np.float64)
+    Fe = None if Fe is None else np.ascontiguousarray(Fe, dtype=np.float64)
+    ud = None if ud is None else np.ascontiguousarray(ud, dtype=np.float64)
+    rowptr = np.zeros(n + 1, dtype=np.int64)
+    args = (d, order, ncomp, _p(nc), _p(Ke), _p(Fe), _p(node_free), free_nodes.shape[0], _p(free_nodes), _p(ud))
+    S.synth_fe_rows(*args, 0, _p(rowptr), None, None, None)
+    np.cumsum(rowptr, out=rowptr)
+    nnz = int(rowptr[-1])
+    col = np.empty(nnz, dtype=np.int32)
+    val = np.empty(nnz, dtype=np.float64)
+    b = np.zeros(n)
+    S.synth_fe_rows(*args, 1, _p(rowptr), _p(col), _p(val), _p(b))
+    return rowptr, col, val, b, n, free_nodes
+
+
+def elasticity_element(h, order=2, lam=1.0, mu=1.0, body=(0.0, 0.0, -1.0)):
+    """element matrix / load of a(u,v) = int lam div(u) div(v) + 2 mu eps(u):eps(v)  (form of
+    test/Applications/Elasticity.jl:31-37; lam = mu = 1 per SURVEY.md 8d), node-major local dofs"""
+    d = len(h)
+    phi, G, w = _tensor_basis(order, d, h, order + 1)
+    nb = phi.shape[1]
+    Ke = np.zeros((nb * d, nb * d))
+    GG = np.einsum("q,qad,qbd->ab", w, G, G)
+    for c1 in range(d):
+        for c2 in range(d):
+            blk = lam * np.einsum("q,qa,qb->ab", w, G[:, :, c1], G[:, :, c2]) + mu * np.einsum("q,qa,qb->ab", w, G[:, :, c2], G[:, :, c1])
+            if c1 == c2:
+                blk = blk + mu * GG
+            Ke[c1::d, c2::d] = blk
+    Fe = np.zeros(nb * d)
+    for c in range(d):
+        Fe[c::d] = body[c] * (w @ phi)
+    return Ke, Fe
+
+
+def elasticity_rows(ncell, order=2, lam=1.0, mu=1.0, body=(0.0, 0.0, -1.0)):
+    """C4 system: (rowptr, col, val, b, n) -- clamped on the face x = 0, constant body force"""
+    d = len(ncell)
+    h = tuple(1.0 / n for n in ncell)
+    Ke, Fe = elasticity_element(h, order, lam, mu, body)
+    nn, mi = _node_grid(ncell, order)
+    rp, col, val, b, n, _ = fe_rows(ncell, order, d, Ke, mi[:, 0] == 0, Fe=Fe)
+    return rp, col, val, b, n
+
+
+def _prolong_1d(order, nc_coarse):
+    """1D nodal interpolation from n cells to 2n cells of the degree-`order` Lagrange space (dense small rows)"""
+    import scipy.sparse as sp
+
+    nf, ncn = 2 * order * nc_coarse + 1, order * nc_coarse + 1
+    rows, cols, vals = [], [], []
+    for i in range(nf):
+        c = min(i // (2 * order), nc_coarse - 1)
+        xi = (i - c * 2 * order) / (2.0 * order)  # exact dyadic reference coordinate
+        N, _ = _lagrange_1d(order, np.array([xi]))
+        for a in range(order + 1):
+            if N[0, a] != 0.0:
+                rows.append(i)
+                cols.append(c * order + a)
+                vals.append(N[0, a])
+    return sp.csr_matrix((vals, (rows, cols)), shape=(nf, ncn))
+
+
+def fe_prolongation(ncell_coarse, order, ncomp, free_nodes_fine, free_nodes_coarse):
+    """P (fine free dofs x coarse free dofs): nodal interpolation with zero Dirichlet values
+    (src/MultilevelTools/GridTransferOperators.jl:391-401), CSR with ascending columns; R = P^T"""
+    import scipy.sparse as sp
+
+    P = _prolong_1d(order, ncell_coarse[0])
+    for k in range(1, len(ncell_coarse)):
+        P = sp.kron(_prolong_1d(order, ncell_coarse[k]), P, format="csr")  # x fastest
+    P = P[free_nodes_fine][:, free_nodes_coarse]
+    if ncomp > 1:
+        P = sp.kron(P, sp.identity(ncomp), format="csr")
+    P = sp.csr_matrix(P)
+    P.eliminate_zeros()
+    P.sort_indices()
+    R = P.T.tocsr()
+    R.sort_indices()
+    return P, R
+
+
+def _triplet(A):
+    return A.indptr.astype(np.int64), A.indices.astype(np.int32), A.data.astype(np.float64)
+
+
+@dataclass
+class SerialLevel:
+    """level descriptor of a single-part (serial) FE hierarchy: what upload_hierarchy needs"""
+    n_own: int
+    n_ghost: int = 0
+    ncell: tuple = None
+
+
+def elasticity_hierarchy_host(ncell_fine, nlevels, order=2, lam=1.0, mu=1.0, body=(0.0, 0.0, -1.0)) -> HostHierarchy:
+    """C4 hierarchy: factor-2 nested meshes, re-discretised level matrices
+    (src/MultilevelTools/FESpaceHierarchies.jl:151-174), nodal prolongations, R = P^T"""
+    d = len(ncell_fine)
+    nc = tuple(int(n) for n in ncell_fine)
+    levels, As, frees, b0 = [], [], [], None
+    for l in range(nlevels):
+        h = tuple(1.0 / n for n in nc)
+        Ke, Fe = elasticity_element(h, order, lam, mu, body)
+        nn, mi = _node_grid(nc, order)
+        rp, col, val, b, n, free_nodes = fe_rows(nc, order, d, Ke, mi[:, 0] == 0, Fe=Fe)
+        if l == 0:
+            b0 = b
+        levels.append(SerialLevel(n, 0, nc))
+        As.append((rp, col, val))
+        frees.append(free_nodes)
+        if l < nlevels - 1:
+            assert all(n % 2 == 0 for n in nc), "factor-2 coarsening needs even cell counts"
+            nc = tuple(n // 2 for n in nc)
+    Ps, Rs = [], []
+    for l in range(nlevels - 1):
+        P, R = fe_prolongation(levels[l + 1].ncell, order, d, frees[l], frees[l + 1])
+        Ps.append(_triplet(P))
+        Rs.append(_triplet(R))
+    return HostHierarchy(levels, As, Ps, Rs, b0)
+
+
+def stokes_cavity_host(ncell, nlevels=1):
+    """C5: 2D lid-driven cavity, Q2 velocity / P1-discontinuous pressure (joss_paper/demo.jl:20-91):
+    A (int grad u : grad v), B (-(div v) p; pressure rows), Bt, pressure mass Mp, rhs from the lid data
+    u = (1,0) on y = 1; with nlevels > 1 the velocity-block hierarchy (mats, P, R) for the GMG block.
+    Everything as CSR triplets (rowptr int64, col int32, val)."""
+    import scipy.sparse as sp
+
+    d, order = 2, 2
+    nc = tuple(int(n) for n in ncell)
+    out = {}
+    mats, frees, cells = [], [], []
+    for l in range(nlevels):
+        h = tuple(1.0 / n for n in nc)
+        phi, G, w = _tensor_basis(order, d, h, 3)
+        Ks = np.einsum("q,qad,qbd->ab", w, G, G)
+        nb = phi.shape[1]
+        Ke = np.zeros((nb * d, nb * d))
+        for c in range(d):
+            Ke[c::d, c::d] = Ks
+        nn, mi = _node_grid(nc, order)
+        bnd = ((mi == 0) | (mi == np.array(nn) - 1)).any(axis=1)
+        ud = None
+        if l == 0:
+            ud = np.zeros((mi.shape[0], d))
+            ud[mi[:, 1] == nn[1] - 1, 0] = 1.0
+            ud = ud.ravel()
+        rp, col, val, b, n, free_nodes = fe_rows(nc, order, d, Ke, bnd, ud=ud)
+        mats.append((rp, col, val))
+        frees.append(free_nodes)
+        cells.append(nc)
+        if l == 0:
+            out.update(A=(rp, col, val), fu=b, n_u=n)
+            # pressure blocks, cell by cell: P1disc basis {1, xi-1/2, eta-1/2} in reference coordinates
+            xi, _ = _gauss01(3)
+            qx, qy = np.tile(xi, 3), np.repeat(xi, 3)
+            psi = np.stack([np.ones(9), qx - 0.5, qy - 0.5], axis=1)
+            Be = np.zeros((3, nb * d))
+            for c in range(d):
+                Be[:, c::d] = -np.einsum("q,qm,qa->ma", w, psi, G[:, :, c])
+            Mpe = np.einsum("q,qm,qn->mn", w, psi, psi)
+            ncell_tot = nc[0] * nc[1]
+            cx, cy = np.arange(ncell_tot) % nc[0], np.arange(ncell_tot) // nc[0]
+            loc = np.arange(nb)
+            conn = ((cy[:, None] * order + loc[None, :] // (order + 1)) * nn[0] + cx[:, None] * order + loc[None, :] % (order + 1))  # ascending
+            vdof = (conn[:, :, None] * d + np.arange(d)[None, None, :]).reshape(ncell_tot, -1)  # global (node, comp) ids
+            node_free = np.full(mi.shape[0], -1, dtype=np.int64)
+            node_free[free_nodes] = np.arange(free_nodes.shape[0])
+            fdof = node_free[conn][:, :, None] * d + np.arange(d)[None, None, :]
+            fdof = np.where(node_free[conn][:, :, None] >= 0, fdof, -1).reshape(ncell_tot, -1)
+            rows = np.repeat(np.arange(ncell_tot * 3).reshape(ncell_tot, 3), nb * d, axis=1).ravel()
+            cols = np.tile(fdof, (1, 3)).ravel()
+            vals = np.tile(Be.ravel(), ncell_tot)
+            keep = cols >= 0
+            B = sp.csr_matrix((vals[keep], (rows[keep], cols[keep])), shape=(ncell_tot * 3, n))
+            B.sort_indices()
+            # fp = -B[:, dirichlet] ud
+            gcols = np.tile(vdof, (1, 3)).ravel()
+            fp = np.zeros(ncell_tot * 3)
+            np.subtract.at(fp, rows[~keep], vals[~keep] * ud[gcols[~keep]])
+            Mp = sp.kron(sp.identity(ncell_tot), Mpe, format="csr")
+            Mp.sort_indices()
+            Bt = B.T.tocsr()
+            Bt.sort_indices()
+            out.update(B=_triplet(B), Bt=_triplet(Bt), Mp=_triplet(Mp), fp=fp, n_p=ncell_tot * 3)
+        if l < nlevels - 1:
+            nc = tuple(n // 2 for n in nc)
+    if nlevels > 1:
+        Ps, Rs = [], []
+        for l in range(nlevels - 1):
+            P, R = fe_prolongation(cells[l + 1], order, d, frees[l], frees[l + 1])
+            Ps.append(_triplet(P))
+            Rs.append(_triplet(R))
+        out.update(mats=mats, P=Ps, R=Rs)
+    return out

@@ -74,6 +74,47 @@ def test_c4_fgmres_gmg_elasticity_q2(gsb, ctx):
     assert H.mats[0].shape[0] % 3 == 0 and H.mats[0][0].nnz % 3 == 0
 
 
+def _bench_parity(gsb, ctx, config, cells):
+    """device solve of a bench.py configuration vs the threaded CPU oracle on the same generated system"""
+    import bench
+
+    prob = bench.Problem(config, cells)
+    solver, ns, x, b = prob.build_device(gsb, ctx)
+    gsb.solve_(x, ns, b)
+    hist_first = solver.log.history()
+    iters_first = solver.log.num_iters
+    _, ohist, oit = bench.oracle_sample(prob, bench.MAXITER, bench.host_threads())
+    assert solver.log.flag == OS.SOLVER_CONVERGED_RTOL
+    assert abs(iters_first - oit) <= 1, (iters_first, oit)
+    n = min(iters_first, oit) + 1
+    return prob, solver, ns, x, b, rel_hist_diff(hist_first[:n], ohist[:n]), iters_first
+
+
+def test_c4_fgmres_gmg_elasticity_q2_32cubed(gsb, ctx):
+    """C4 at 32^3 Q2 cells (823 k dofs, 155 M non-zeros, 4 levels): FGMRES(30)+GMG against the threaded oracle --
+    identical iteration count and relative residual history to 1e-10; the fine matrix must be stored as sorted
+    3x3 block-SELL (the long-row format) and its CSR arrays released"""
+    prob, solver, ns, x, b, d, iters = _bench_parity(gsb, ctx, "c4", 32)
+    f = prob.fine.format()
+    assert f["kind"] == "bsell32" and f["block_size"] == 3 and f["sorted"]
+    assert f["stored_entries"] <= 1.10 * prob.level_nnz[0]
+    assert f["bytes_per_pass"] < 0.78 * 12 * prob.level_nnz[0]  # 8.44 B per non-zero + padding vs CSR's 12
+    assert d < 1e-10, d
+    # true residual of the device solution on the generated system
+    from util import host_to_scipy
+
+    A = host_to_scipy(prob.hh.A[0], prob.n_own)
+    assert np.linalg.norm(A @ x.get() - prob.b) <= 2e-8 * np.linalg.norm(prob.b)
+
+
+def test_c5_gmres_block_triangular_stokes_256(gsb, ctx):
+    """C5 at full size (256^2 Q2-P1disc cells, 522 k velocity + 197 k pressure dofs, 6 velocity levels): GMRES(30)
+    right-preconditioned by the block-triangular solver of joss_paper/demo.jl against the threaded oracle"""
+    prob, solver, ns, x, b, d, iters = _bench_parity(gsb, ctx, "c5", 256)
+    assert prob.fine.format()["block_size"] == 2
+    assert d < 1e-8, d  # inner CG / GMG iterations amplify reduction-order differences: 1e-8 on the relative history
+
+
 def _stokes_pair(gsb, ctx, outer):
     nlev = 2
     st = fem.stokes_cavity((16, 16), nlevels=nlev)
