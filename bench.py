@@ -397,9 +397,15 @@ def main():
         sync = barrier if distributed else (lambda: c.synchronize())
         mx = max_over_ranks if distributed else (lambda v: v)
         # ---- device-resident timing: inputs already in HBM
+        hist_first = None
         for _ in range(warmup):
             x.fill(0.0)
             gsb.solve_(x, ns, b)
+            if hist_first is None:
+                # the parity record uses the FIRST solve after set-up: the block solvers warm-start their inner
+                # iterative solvers from the previous solve's caches (reference quirk, BlockTriangularSolvers.jl:
+                # 188-242: the y caches are zeroed at set-up only), so later solves follow a different history
+                hist_first = solver.log.history()
         sampler = ClockSampler(local_rank)
         sync()
         if rank == 0:
@@ -418,7 +424,7 @@ def main():
         clocks = sampler.stop() if rank == 0 else None
         launches = c.launch_count() - l0
         out = dict(prob=prob, ms=mx(dev_ms / steps), wall_ms=wall_ms / steps, iters=solver.log.num_iters, iters_seen=iters_seen,
-                   hist=solver.log.history(), flag=solver.log.flag, launches=launches // steps, clocks=clocks)
+                   hist=solver.log.history(), hist_first=hist_first, flag=solver.log.flag, launches=launches // steps, clocks=clocks)
         # ---- end-to-end through the host-buffer C-ABI entry point (pinned host memory, x0 = 0 not uploaded)
         if with_e2e:
             n = prob.n_own
@@ -564,12 +570,12 @@ def main():
         k = SAMPLE_ITERS[cfg]
         dt, ohist, oit = oracle_sample(prob, k, threads)
         est = dt * res["iters"] / max(oit, 1)
-        d = rel_hist_diff(res["hist"][: oit + 1], ohist)
+        d = rel_hist_diff(res["hist_first"][: oit + 1], ohist)
         line["cpu_baseline"] = {"value": round(n_glob / est / 1e6, 4), "unit": "MDOF/s", "cores": threads, "kind": "port",
                                 "est_solve_time_ms": round(est * 1e3, 1),
                                 "sample": f"{oit} outer iterations (of {res['iters']}) of the same {prob.name} system on the oracle port with "
                                           f"{threads} OpenMP threads, scaled by {res['iters']}/{oit}"}
-        line["parity"] = {"against": "CPU restatement (oracle/) on the same assembled system", "iterations_compared": oit,
+        line["parity"] = {"against": "CPU restatement (oracle/) on the same assembled system; first solve after set-up on both sides", "iterations_compared": oit,
                           "rel_residual_history_max_diff": d, "ok": bool(d < 1e-10)}
     if parity is not None:
         line["parity"] = parity

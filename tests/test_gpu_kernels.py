@@ -25,10 +25,10 @@ KERNELS = ["vector", "sell", "sell_sorted"]
 
 
 def _select(ctx, kernel):
-    """row-kernel family for the matrices created next: CSR fallback kernel, block-SELL-32, block-SELL-32 with the
-    rows sorted by length inside windows of 256 (forced, even where the planner would not sort)"""
+    """row-kernel family for the matrices created next: CSR fallback kernel, block-SELL-32 in natural row order
+    (sorting forced off), block-SELL-32 with the rows sorted by length inside windows of 256 (forced on)"""
     ctx.set_option("spmv", "vector" if kernel == "vector" else "auto")
-    ctx.set_option("sell_sort", "1" if kernel == "sell_sorted" else "auto")
+    ctx.set_option("sell_sort", "1" if kernel == "sell_sorted" else ("0" if kernel == "sell" else "auto"))
 
 
 def _reset(ctx):
