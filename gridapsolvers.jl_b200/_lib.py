@@ -32,7 +32,7 @@ SIGNATURES = {
     "gsb_timer_stop": [c_p, PP(ctypes.c_float)],
     "gsb_launch_count": [c_p, PP(c_i64)],
     "gsb_set_option": [c_p, ctypes.c_char_p, ctypes.c_char_p],
-    "gsb_diag_sell_plan": [c_i64, c_i64, c_i64, c_p, c_p, c_i, c_i, c_p, c_p, c_p],
+    "gsb_diag_sell_plan": [c_i64, c_i64, c_i64, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p],
     "gsb_bench_rows": [c_p, c_i, c_i, PP(ctypes.c_float)],
     "gsb_profile_start": [c_p],
     "gsb_profile_stop": [c_p, c_i, PP(c_i), c_p, c_p, c_p, c_p, c_p, c_p],

@@ -247,9 +247,9 @@ void sell_fill(gsb_mat_t A, bool values_only, const double *dval) {
   const int *perm = A->sorted ? A->sell_perm.p : nullptr;
   const int vo = values_only ? 1 : 0;
   switch (A->bs) {
-    case 1: sell_fill_kernel<1><<<grid, 256, 0, ctx->stream>>>(npos, A->n_brows, perm, A->sell_off.p, A->rowptr.p, A->col.p, dval, A->sell_bcol.p, A->sell_val.p, vo); break;
-    case 2: sell_fill_kernel<2><<<grid, 256, 0, ctx->stream>>>(npos, A->n_brows, perm, A->sell_off.p, A->rowptr.p, A->col.p, dval, A->sell_bcol.p, A->sell_val.p, vo); break;
-    case 3: sell_fill_kernel<3><<<grid, 256, 0, ctx->stream>>>(npos, A->n_brows, perm, A->sell_off.p, A->rowptr.p, A->col.p, dval, A->sell_bcol.p, A->sell_val.p, vo); break;
+    case 1: sell_fill_kernel<1><<<grid, 256, 0, ctx->stream>>>(npos, A->n_brows, perm, A->sell_lmask.p, A->sell_off.p, A->sell_kbase.p, A->rowptr.p, A->col.p, dval, A->sell_bcol.p, A->sell_val.p, vo); break;
+    case 2: sell_fill_kernel<2><<<grid, 256, 0, ctx->stream>>>(npos, A->n_brows, perm, A->sell_lmask.p, A->sell_off.p, A->sell_kbase.p, A->rowptr.p, A->col.p, dval, A->sell_bcol.p, A->sell_val.p, vo); break;
+    case 3: sell_fill_kernel<3><<<grid, 256, 0, ctx->stream>>>(npos, A->n_brows, perm, A->sell_lmask.p, A->sell_off.p, A->sell_kbase.p, A->rowptr.p, A->col.p, dval, A->sell_bcol.p, A->sell_val.p, vo); break;
     default: fail(GSB_EINVAL, "block-SELL: unsupported block size");
   }
   launched(ctx);
@@ -435,7 +435,7 @@ static void launch_sell_list(gsb_mat_t A, RowArgs &a, const int *list, int64_t n
   if (n_list == 0 && MODE != ROW_SPMV_DOT) return;
   const int64_t grid = std::max<int64_t>(1, (n_list * 32 + SELL_THREADS - 1) / SELL_THREADS);
   if (MODE == ROW_SPMV_DOT) GSB_CHECK((size_t)grid <= PARTIALS_CAP, "matrix too large for the fused dot");
-  SellArgs m{list, n_list, A->sell_perm.p, A->sell_blen.p, A->sell_off.p, A->sell_bcol.p, A->sell_val.p, A->n_brows};
+  SellArgs m{list, n_list, A->sell_perm.p, A->sell_lmask.p, A->sell_off.p, A->sell_kbase.p, A->sell_bcol.p, A->sell_val.p, A->n_brows};
   const int variant = std::stoi(ctx->opt("sell_variant", "0"));
   const unsigned g = (unsigned)grid;
   switch (A->bs * 2 + (A->sorted ? 1 : 0)) {

@@ -160,7 +160,9 @@ struct gsb_mat_s {
   bool sorted = false;
   int64_t n_brows = 0, n_slices = 0;
   int64_t sell_blocks = 0;  // stored blocks incl. padding
-  gsb::DevBuf<int> sell_perm, sell_blen, sell_off, sell_bcol;
+  int64_t sell_explicit = 0;  // (slice, k) pairs whose 32 block-column ids are stored explicitly (the others are affine)
+  int64_t sell_aligned = 0;   // diagonal-aligned slices (all their column words are affine)
+  gsb::DevBuf<int> sell_perm, sell_lmask, sell_off, sell_kbase, sell_bcol;
   gsb::DevBuf<double> sell_val;
   // halo overlap: slices whose rows touch no ghost column ("interior") run while the exchange is in
   // flight, the remaining ("boundary") slices after it

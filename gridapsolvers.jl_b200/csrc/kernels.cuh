@@ -194,7 +194,12 @@ __device__ __forceinline__ void row_epilogue_pre(const RowArgs &a, int64_t row, 
 //     (Q2 elements: 125/75/45/27-node stencils alternate along a mesh line) the block rows are sorted by
 //     length inside windows of 256 block rows (SELL-C-sigma with C = 32, sigma = 256) and `perm` maps a
 //     (slice, lane) position to its block row; padding lanes have perm = -1.
-//   * bytes per stored non-zero: 8 + 4/BS^2 (value + shared block-column id) instead of CSR's 12.
+//   * block-column ids are compressed per (slice, k): when the k-th blocks of the 32 lanes of a slice sit in
+//     CONSECUTIVE block columns (base + lane: the rule on a mesh-ordered matrix -- the k-th neighbours of 32
+//     consecutive rows are 32 consecutive columns) only `base` is stored (kbase[] >= 0, 4 B per 32 blocks);
+//     otherwise kbase[] = ~e and the 32 ids are line e of bcol[] (explicit).  On the C2 fine level 83 % of the
+//     (slice, k) pairs are affine: 8.8 B per stored non-zero instead of 12.
+//   * bytes per stored non-zero: 8 + (0.125 .. 4.125)/BS^2 instead of CSR's 12.
 // Arithmetic: lane-sequential, ascending column order inside every row, product rounded before the add
 // (__dmul_rn/__dadd_rn) -- row i of a block row visits block k = 0,1,.. and inside a block column
 // j = 0..BS-1, i.e. exactly the CSR order of that row => bit-identical to the oracle's sequential CSR
@@ -215,14 +220,24 @@ __device__ __forceinline__ double ldg_nc_f64(const double *p) {
   asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
+__device__ __forceinline__ int ldg_nc_s32(const int *p) {
+  int v;
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+// block column of this lane for a (slice, k) pair whose kbase word is kb (warp-uniform => no divergence)
+__device__ __forceinline__ int sell_bcol_of(int kb, int lane, const int *__restrict__ bcol) {
+  return kb >= 0 ? kb + lane : ldg_stream_s32(bcol + (((size_t)(~kb)) << 5) + lane);
+}
 
 struct SellArgs {
   const int *slice_list;  // optional indirection: the slices this launch processes (nullptr = all)
   int64_t n_list;         // number of slices this launch processes
   const int *perm;        // PERM only: block row of every (slice, lane) position, -1 = padding lane
-  const int *blen;        // blocks per block row, indexed by position (padded with 0)
+  const int *lmask;       // per position: slice width <= 32: bit k set <=> the lane has a block in slot k; else its length
   const int *slice_off;   // per slice: offset of the slice in units of 32 blocks; nslices+1 entries
-  const int *bcol;        // block-column ids, column-major per slice
+  const int *kbase;       // per (slice, k): >= 0 affine base block column (lane l reads base + l), < 0: ~line of bcol
+  const int *bcol;        // explicit block-column ids, one 32-lane line per non-affine (slice, k)
   const double *val;      // BS*BS values per block, each (k, i, j) a 32-lane line
   int64_t n_brows;        // number of block rows
 };
@@ -246,9 +261,11 @@ __global__ void __launch_bounds__(THREADS, MINB) sell_kernel(SellArgs m, RowArgs
     } else {
       valid = pos < m.n_brows;
     }
-    const int len = m.blen[pos];
+    const int lm = m.lmask[pos];
     const int so0 = m.slice_off[slice], so1 = m.slice_off[slice + 1];
-    const int width = so1 - so0;  // blocks per lane in this slice (warp-uniform)
+    const int width = so1 - so0;  // slots per lane in this slice (warp-uniform)
+    const bool wide = width > 32;
+    auto slot_on = [&](int k) { return wide ? (k < lm) : (((unsigned)lm >> k) & 1u) != 0u; };
     RowPre<MODE> pre{};
     double s[BS];
 #pragma unroll
@@ -258,28 +275,32 @@ __global__ void __launch_bounds__(THREADS, MINB) sell_kernel(SellArgs m, RowArgs
 #pragma unroll
       for (int i = 0; i < BS; ++i) s[i] = row_init<MODE>(a, brow * BS + i);
     }
-    const int *cp = m.bcol + ((size_t)so0 << 5) + lane;
+    const int *kp = m.kbase + so0;
     const double *vp = m.val + (((size_t)so0 * BB) << 5) + lane;
     const double al = a.alpha;
     int k = 0;
     for (; k + U <= width; k += U) {
       int cc[U];
       double vv[U][BB], xv[U][BS];
-      // burst order: all block-column ids, then all values (contiguous bursts per warp), then the gathers
+      // burst order: all column words, then all values (contiguous bursts per warp), then the gathers
 #pragma unroll
-      for (int u = 0; u < U; ++u) cc[u] = ldg_stream_s32(cp + (size_t)(k + u) * 32);
+      for (int u = 0; u < U; ++u) cc[u] = ldg_nc_s32(kp + k + u);
 #pragma unroll
       for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int e = 0; e < BB; ++e) vv[u][e] = ldg_stream_f64(vp + ((size_t)(k + u) * BB + e) * 32);
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
+      for (int u = 0; u < U; ++u) cc[u] = sell_bcol_of(cc[u], lane, m.bcol);
+      bool on[U];
 #pragma unroll
-        for (int j = 0; j < BS; ++j) xv[u][j] = ldg_nc_f64(a.x + (size_t)cc[u] * BS + j);
+      for (int u = 0; u < U; ++u) {
+        on[u] = slot_on(k + u);  // masked slots gather nothing (their column word may point outside x)
+#pragma unroll
+        for (int j = 0; j < BS; ++j) xv[u][j] = on[u] ? ldg_nc_f64(a.x + (int64_t)cc[u] * BS + j) : 0.0;
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        if (k + u < len) {
+        if (on[u]) {
           double t[BS];
 #pragma unroll
           for (int j = 0; j < BS; ++j) t[j] = (MODE == ROW_SPMV) ? __dmul_rn(xv[u][j], al) : xv[u][j];
@@ -291,13 +312,14 @@ __global__ void __launch_bounds__(THREADS, MINB) sell_kernel(SellArgs m, RowArgs
       }
     }
     for (; k < width; ++k) {
-      const int c = ldg_stream_s32(cp + (size_t)k * 32);
+      const int c = sell_bcol_of(ldg_nc_s32(kp + k), lane, m.bcol);
       double vv[BB], xv[BS];
 #pragma unroll
       for (int e = 0; e < BB; ++e) vv[e] = ldg_stream_f64(vp + ((size_t)k * BB + e) * 32);
+      const bool on = slot_on(k);
 #pragma unroll
-      for (int j = 0; j < BS; ++j) xv[j] = ldg_nc_f64(a.x + (size_t)c * BS + j);
-      if (k < len) {
+      for (int j = 0; j < BS; ++j) xv[j] = on ? ldg_nc_f64(a.x + (int64_t)c * BS + j) : 0.0;
+      if (on) {
 #pragma unroll
         for (int j = 0; j < BS; ++j)
           if (MODE == ROW_SPMV) xv[j] = __dmul_rn(xv[j], al);
@@ -323,13 +345,16 @@ __global__ void __launch_bounds__(THREADS, MINB) sell_kernel(SellArgs m, RowArgs
 }
 
 // CSR -> block-SELL conversion on the device: one lane per (slice, lane) position copies its block row
-// into the slice (coalesced writes; padding written as zero blocks with block column 0).
+// into the slice (coalesced writes; padding written as zero blocks; explicit id lines get block column 0
+// in their padding lanes, affine (slice, k) pairs store no ids at all -- kbase[] comes from the host plan).
 // values_only: refresh of the values after gsb_mat_update_values (same sparsity).
 template <int BS>
 __global__ void __launch_bounds__(256) sell_fill_kernel(int64_t npos, int64_t n_brows, const int *__restrict__ perm,
-                                                        const int *__restrict__ slice_off, const int *__restrict__ rowptr,
-                                                        const int *__restrict__ col, const double *__restrict__ val,
-                                                        int *__restrict__ bcol, double *__restrict__ sval, int values_only) {
+                                                        const int *__restrict__ lmask, const int *__restrict__ slice_off,
+                                                        const int *__restrict__ kbase,
+                                                        const int *__restrict__ rowptr, const int *__restrict__ col,
+                                                        const double *__restrict__ val, int *__restrict__ bcol,
+                                                        double *__restrict__ sval, int values_only) {
   constexpr int BB = BS * BS;
   const int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (pos >= npos) return;
@@ -338,21 +363,25 @@ __global__ void __launch_bounds__(256) sell_fill_kernel(int64_t npos, int64_t n_
   const int64_t brow = perm ? (int64_t)perm[pos] : (pos < n_brows ? pos : -1);
   const int so0 = slice_off[slice], width = slice_off[slice + 1] - so0;
   int e0[BS] = {};
-  int nb = 0;
   if (brow >= 0) {
 #pragma unroll
     for (int i = 0; i < BS; ++i) e0[i] = rowptr[brow * BS + i];
-    nb = (rowptr[brow * BS + 1] - e0[0]) / BS;
   }
-  int *cp = bcol + ((size_t)so0 << 5) + lane;
+  const int lm = brow >= 0 ? lmask[pos] : 0;
+  const bool wide = width > 32;
   double *vp = sval + (((size_t)so0 * BB) << 5) + lane;
+  int q = 0;  // next block of the block row (slots are filled in ascending column order)
   for (int k = 0; k < width; ++k) {
-    const bool in = k < nb;
-    if (!values_only) cp[(size_t)k * 32] = in ? col[e0[0] + k * BS] / BS : 0;
+    const bool in = wide ? (k < lm) : (((unsigned)lm >> k) & 1u) != 0u;
+    if (!values_only) {
+      const int kb = kbase[so0 + k];
+      if (kb < 0) bcol[(((size_t)(~kb)) << 5) + lane] = in ? col[e0[0] + q * BS] / BS : 0;
+    }
 #pragma unroll
     for (int i = 0; i < BS; ++i)
 #pragma unroll
-      for (int j = 0; j < BS; ++j) vp[((size_t)k * BB + i * BS + j) * 32] = in ? val[e0[i] + k * BS + j] : 0.0;
+      for (int j = 0; j < BS; ++j) vp[((size_t)k * BB + i * BS + j) * 32] = in ? val[e0[i] + q * BS + j] : 0.0;
+    if (in) ++q;
   }
 }
 

@@ -21,8 +21,9 @@ int64_t gsb_mat_s::format_bytes() const {
       if (b) t += b->format_bytes();
     return t;
   }
-  if (sell_ok)  // values + block-column ids + per-position length (+ permutation) + slice offsets
-    return sell_blocks * ((int64_t)bs * bs * 8 + 4) + n_slices * 32 * (sorted ? 8 : 4) + (n_slices + 1) * 4;
+  if (sell_ok)  // values + column words (one per 32 blocks) + explicit id lines + per-position length (+ permutation) + slice offsets
+    return sell_blocks * ((int64_t)bs * bs * 8) + (sell_blocks / 32) * 4 + sell_explicit * 128 + n_slices * 32 * (sorted ? 8 : 4) +
+           (n_slices + 1) * 4;
   return nnz * 12 + (n_rows + 1) * 4;
 }
 
@@ -80,13 +81,16 @@ struct SellPlan {
   bool ok = false;
   int bs = 1;
   bool sorted = false;
-  int64_t n_brows = 0, n_slices = 0, blocks = 0, sum_blocks = 0;
-  std::vector<int> perm, blen, off;      // perm empty when !sorted; blen by position, padded with 0
+  int64_t n_brows = 0, n_slices = 0, blocks = 0, sum_blocks = 0, n_explicit = 0;
+  int64_t aligned_slices = 0;
+  std::vector<int> perm, blen, off;      // perm empty when !sorted; blen by position (blocks per block row), padded with 0
+  std::vector<int> lmask;                // per position: validity word of its slots (bit mask, or length when width > 32)
+  std::vector<int> kbase;                // per (slice, k): affine base block column, or ~(explicit line)
   std::vector<int> int_slices, bnd_slices;
 };
 
 SellPlan plan_sell(int64_t n_rows, int64_t n_own_cols, int64_t n_ghost_cols, const int *rowptr, const int *col, bool detect_blocks,
-                   const std::string &sort_opt) {
+                   const std::string &sort_opt, bool affine = true, bool dia = true) {
   SellPlan P;
   if (n_rows == 0) return P;
   const int64_t n_cols = n_own_cols + n_ghost_cols;
@@ -138,7 +142,43 @@ SellPlan plan_sell(int64_t n_rows, int64_t n_own_cols, int64_t n_ghost_cols, con
       perm.clear();
     }
   }
-  const int64_t tot = sorted ? padded_total(blen) : tot_unsorted;
+  // ---- per-slice layout.  PACKED slice: lane stores its blocks k = 0..len-1, width = longest block row.
+  // DIAGONAL-ALIGNED slice (unsorted matrices): the k-slots of the slice are the distinct diagonal offsets
+  // d = (block column) - (slice*32 + lane) of its lanes in ascending order; a lane fills the slots whose offset
+  // it has, in ascending order = its CSR order, the other slots are masked out.  Every (slice, k) pair of an
+  // aligned slice is affine (block column = slice*32 + d_k + lane): a mesh-ordered stencil matrix stores one
+  // word per 32 blocks instead of 32 ids, including the slices that cross mesh-line ends.  A slice is aligned
+  // when it has at most 32 distinct offsets and aligning costs at most 25 % more slots than packing.
+  std::vector<int> width((size_t)nsl, 0);
+  std::vector<unsigned char> aligned((size_t)nsl, 0);
+  std::vector<std::vector<int>> offs(dia && !sorted ? (size_t)nsl : 0);
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int64_t sl = 0; sl < nsl; ++sl) {
+    int w = 0;
+    for (int l = 0; l < 32; ++l) w = std::max(w, blen[(size_t)(sl * 32 + l)]);
+    width[(size_t)sl] = w;
+    if (!dia || sorted || w == 0) continue;
+    int64_t d[32 * 48];
+    int nd = 0;
+    bool too_many = false;
+    for (int l = 0; l < 32 && !too_many; ++l) {
+      const int64_t b = sl * 32 + l;
+      if (b >= nb) break;
+      const int e0 = rowptr[b * BS], L = blen[(size_t)b];
+      if (L > 32) { too_many = true; break; }
+      for (int q = 0; q < L; ++q) d[nd++] = (int64_t)(col[(size_t)e0 + (size_t)q * BS] / BS) - b;
+    }
+    if (too_many) continue;
+    std::sort(d, d + nd);
+    nd = (int)(std::unique(d, d + nd) - d);
+    if (nd > 32 || nd * 4 > w * 5) continue;
+    aligned[(size_t)sl] = 1;
+    width[(size_t)sl] = nd;
+    offs[(size_t)sl].assign(d, d + nd);
+  }
+  int64_t tot = 0;
+  for (int64_t sl = 0; sl < nsl; ++sl) tot += width[(size_t)sl];
+  tot *= 32;
   P.bs = BS; P.sorted = sorted; P.n_brows = nb; P.n_slices = nsl; P.blocks = tot; P.sum_blocks = sum;
   // padding budget: 25 %; very short rows (prolongations: 1/2/4/8 entries) may pad up to 3x -- a padded
   // coalesced slice still beats the row-pointer-chasing CSR kernel there
@@ -146,10 +186,75 @@ SellPlan plan_sell(int64_t n_rows, int64_t n_own_cols, int64_t n_ghost_cols, con
   const double pad_ok = (avg <= 8.0) ? 3.0 : 1.25;
   if (tot / 32 >= INT32_MAX || (double)tot > pad_ok * (double)std::max<int64_t>(sum, 1) + 4096.0) return P;
   P.off.assign((size_t)nsl + 1, 0);
-  for (int64_t sl = 0; sl < nsl; ++sl) {
-    int w = 0;
-    for (int l = 0; l < 32; ++l) w = std::max(w, blen[(size_t)(sl * 32 + l)]);
-    P.off[(size_t)sl + 1] = P.off[(size_t)sl] + w;
+  for (int64_t sl = 0; sl < nsl; ++sl) P.off[(size_t)sl + 1] = P.off[(size_t)sl] + width[(size_t)sl];
+  // column words + per-position validity word (lmask): width <= 32: bit k set <=> the lane has a block in slot
+  // k; width > 32 (packed only): the number of blocks of the lane
+  {
+    P.kbase.assign((size_t)P.off[(size_t)nsl], -1);
+    P.lmask.assign((size_t)npos, 0);
+#pragma omp parallel for schedule(static)
+    for (int64_t sl = 0; sl < nsl; ++sl) {
+      const int w = width[(size_t)sl];
+      int *kb = P.kbase.data() + P.off[(size_t)sl];
+      if (aligned[(size_t)sl]) {
+        const std::vector<int> &d = offs[(size_t)sl];
+        for (int k = 0; k < w; ++k) kb[k] = (int)(sl * 32 + d[(size_t)k]);  // may be < 0: see the fix-up below
+        for (int l = 0; l < 32; ++l) {
+          const int64_t b = sl * 32 + l;
+          if (b >= nb) break;
+          const int e0 = rowptr[b * BS], L = blen[(size_t)b];
+          unsigned m = 0;
+          int k = 0;
+          for (int q = 0; q < L; ++q) {
+            const int dq = (int)((int64_t)(col[(size_t)e0 + (size_t)q * BS] / BS) - b);
+            while (d[(size_t)k] != dq) ++k;
+            m |= 1u << k;
+          }
+          P.lmask[(size_t)b] = (int)m;
+        }
+        continue;
+      }
+      int e0[32], ln[32];
+      for (int l = 0; l < 32; ++l) {
+        const int64_t pos = sl * 32 + l;
+        const int64_t b = sorted ? perm[(size_t)pos] : (pos < nb ? pos : -1);
+        ln[l] = b < 0 ? 0 : blen[(size_t)pos];
+        e0[l] = b < 0 ? 0 : rowptr[b * BS];
+        P.lmask[(size_t)pos] = w <= 32 ? (int)(ln[l] >= 32 ? 0xffffffffu : ((1u << ln[l]) - 1u)) : ln[l];
+      }
+      for (int k = 0; k < w && affine; ++k) {
+        bool any = false, ok = true;
+        int64_t base = 0;
+        for (int l = 0; l < 32 && ok; ++l) {
+          if (k >= ln[l]) continue;
+          const int64_t c = col[(size_t)e0[l] + (size_t)k * BS] / BS;
+          if (!any) { base = c - l; any = true; }
+          else if (c - l != base) ok = false;
+        }
+        if (any && ok && base >= 0) kb[k] = (int)base;
+      }
+    }
+    // a negative word means "explicit line": affine bases of aligned slices that are negative (first slices:
+    // slot offsets reach before column 0 for the lanes that do not use them) are stored biased instead
+    int64_t nexp = 0;
+    for (int64_t sl = 0; sl < nsl; ++sl) {
+      int *kb = P.kbase.data() + P.off[(size_t)sl];
+      const int w = width[(size_t)sl];
+      if (aligned[(size_t)sl]) {
+        bool neg = false;
+        for (int k = 0; k < w; ++k) neg = neg || kb[k] < 0;
+        if (!neg) continue;
+        // rare (only the first few slices): fall back to explicit lines for the negative slots
+        for (int k = 0; k < w; ++k)
+          if (kb[k] < 0) kb[k] = (int)~nexp++;
+        continue;
+      }
+      for (int k = 0; k < w; ++k)
+        if (kb[k] < 0) kb[k] = (int)~nexp++;
+    }
+    P.n_explicit = nexp;
+    P.aligned_slices = 0;
+    for (int64_t sl = 0; sl < nsl; ++sl) P.aligned_slices += aligned[(size_t)sl];
   }
   // interior / boundary slice lists (only for matrices with ghost columns): a slice is "boundary" when one
   // of its block rows references a ghost column (columns ascend: the last one decides)
@@ -180,21 +285,24 @@ void build_sell(gsb_mat_s *A, const int *rowptr, const int *col) {
   A->split_ok = false;
   if (A->n_rows == 0 || ctx->opt("sell", "1") != "1") return;
   SellPlan P = plan_sell(A->n_rows, A->n_own_cols, A->n_ghost_cols, rowptr, col, ctx->opt("block", "1") == "1",
-                         ctx->opt("sell_sort", "auto"));
+                         ctx->opt("sell_sort", "auto"), ctx->opt("sell_affine", "1") == "1", ctx->opt("sell_align", "1") == "1");
   if (!P.ok) return;
   A->bs = P.bs;
   A->sorted = P.sorted;
   A->n_brows = P.n_brows;
   A->n_slices = P.n_slices;
   A->sell_blocks = P.blocks;
+  A->sell_explicit = P.n_explicit;
+  A->sell_aligned = P.aligned_slices;
   auto up = [&](DevBuf<int> &d, const std::vector<int> &h) {
     d.alloc(std::max<size_t>(1, h.size()));
     if (!h.empty()) GSB_CUDA(cudaMemcpy(d.p, h.data(), sizeof(int) * h.size(), cudaMemcpyHostToDevice));
   };
-  up(A->sell_blen, P.blen);
+  up(A->sell_lmask, P.lmask);
   up(A->sell_off, P.off);
   if (P.sorted) up(A->sell_perm, P.perm);
-  A->sell_bcol.alloc((size_t)std::max<int64_t>(P.blocks, 1));
+  up(A->sell_kbase, P.kbase);
+  A->sell_bcol.alloc((size_t)std::max<int64_t>(P.n_explicit * 32, 1));
   A->sell_val.alloc((size_t)std::max<int64_t>(P.blocks, 1) * P.bs * P.bs);
   sell_fill(A, /*values_only=*/false, A->val.p);
   A->sell_ok = true;
@@ -393,21 +501,26 @@ int gsb_mat_destroy(gsb_mat_t A) {
 }
 
 // diagnostics (pure host, no device needed): the block-SELL plan the library would build for a CSR matrix
-// (int32, 0-based, ascending columns).  out[8] = {ok, block size, sorted, block rows, slices, stored blocks incl.
-// padding, blocks without padding, boundary slices}; pos_row (n_slices*32 ints or NULL) receives the block row
-// of every (slice, lane) position (-1 = padding lane), pos_len its length in blocks
+// (int32, 0-based, ascending columns).  out[12] = {ok, block size, sorted, block rows, slices, stored blocks incl.
+// padding, blocks without padding, boundary slices, explicit (slice,k) id lines, (slice,k) pairs, diagonal-aligned
+// slices, 0}; pos_row (n_slices*32 ints or NULL) receives the block row of every (slice, lane) position (-1 =
+// padding lane), pos_len its length in blocks, pos_mask its slot-validity word, col_words (out[9] ints or NULL) the
+// column word of every (slice, k) pair (>= 0: affine base)
 int gsb_diag_sell_plan(int64_t n_rows, int64_t n_own_cols, int64_t n_ghost_cols, const int *rowptr, const int *col,
-                       int detect_blocks, int sort_mode, int64_t *out, int *pos_row, int *pos_len) {
+                       int detect_blocks, int sort_mode, int64_t *out, int *pos_row, int *pos_len, int *pos_mask, int *col_words) {
   API_BEGIN
   GSB_CHECK(rowptr && col && out && n_rows >= 0, "sell plan: bad arguments");
   SellPlan P = plan_sell(n_rows, n_own_cols, n_ghost_cols, rowptr, col, detect_blocks != 0,
                          sort_mode < 0 ? "auto" : (sort_mode ? "1" : "0"));
   out[0] = P.ok; out[1] = P.bs; out[2] = P.sorted; out[3] = P.n_brows; out[4] = P.n_slices; out[5] = P.blocks;
-  out[6] = P.sum_blocks; out[7] = (int64_t)P.bnd_slices.size();
+  out[6] = P.sum_blocks; out[7] = (int64_t)P.bnd_slices.size(); out[8] = P.n_explicit; out[9] = (int64_t)P.kbase.size();
+  out[10] = P.aligned_slices; out[11] = 0;
   if (P.ok) {
+    if (col_words) std::copy(P.kbase.begin(), P.kbase.end(), col_words);
     for (int64_t pos = 0; pos < P.n_slices * 32; ++pos) {
       if (pos_row) pos_row[pos] = P.sorted ? P.perm[(size_t)pos] : (pos < P.n_brows ? (int)pos : -1);
       if (pos_len) pos_len[pos] = P.blen[(size_t)pos];
+      if (pos_mask) pos_mask[pos] = P.lmask[(size_t)pos];
     }
   }
   API_END(nullptr)

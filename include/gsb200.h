@@ -69,11 +69,14 @@ int gsb_profile_start(gsb_ctx_t ctx);
 int gsb_profile_stop(gsb_ctx_t ctx, int cap, int *n_out, int *mode, int *stream_kernel, int64_t *nrows, int64_t *nnz,
                      int *count, double *total_ms);
 /* diagnostics (pure host): the block-SELL-32 plan the library builds for a CSR matrix (int32, 0-based, ascending
- * columns): out[8] = {ok, block size, sorted, block rows, slices, stored blocks incl. padding, blocks without
- * padding, boundary slices}; pos_row / pos_len (n_slices*32 ints or NULL): block row (-1 = padding lane) and
- * length in blocks of every (slice, lane) position.  sort_mode: -1 auto, 0 never, 1 always */
+ * columns): out[12] = {ok, block size, sorted, block rows, slices, stored blocks incl. padding, blocks without
+ * padding, boundary slices, explicit column-id lines, (slice,k) pairs, diagonal-aligned slices, 0}; pos_row / pos_len
+ * / pos_mask (n_slices*32 ints or NULL): block row (-1 = padding lane), length in blocks and slot-validity word (slice
+ * width <= 32: bit k set <=> slot k holds a block; else the length) of every (slice, lane) position; col_words (one
+ * int per (slice,k) pair = stored blocks / 32, or NULL): >= 0 the affine base block column (lane l uses base + l),
+ * < 0 the complement of the explicit id line.  sort_mode: -1 auto, 0 never, 1 always */
 int gsb_diag_sell_plan(int64_t n_rows, int64_t n_own_cols, int64_t n_ghost_cols, const int *rowptr, const int *col,
-                       int detect_blocks, int sort_mode, int64_t *out, int *pos_row, int *pos_len);
+                       int detect_blocks, int sort_mode, int64_t *out, int *pos_row, int *pos_len, int *pos_mask, int *col_words);
 /* diagnostics: average duration of `reps` back-to-back launches of one row-kernel mode on scratch vectors */
 int gsb_bench_rows(gsb_mat_t A, int mode, int reps, float *avg_ms);
 /* runtime knobs (also read from the environment variable GSB_OPTIONS="k=v,k=v" at gsb_init); for tests/tuning:

@@ -223,7 +223,7 @@ def test_spmv_unsorted_rows_and_empty_rows(gsb, ctx):
 
 
 @pytest.mark.parametrize("G_rows", [60, 200])  # average row length; the CSR fallback kernel uses 4 / 16 lanes per row
-@pytest.mark.parametrize("kernel", ["vector", "sell"])
+@pytest.mark.parametrize("kernel", ["vector", "sell_auto"])
 def test_spmv_long_rows(gsb, ctx, G_rows, kernel):
     _select(ctx, kernel)
     try:
@@ -236,7 +236,7 @@ def test_spmv_long_rows(gsb, ctx, G_rows, kernel):
         gsb.mul_(yd, Ad, xd)
         yo = np.zeros(n)
         ola.mul(yo, ola.CSR(A), x)
-        if kernel == "sell":
+        if kernel == "sell_auto":
             # random row lengths: sorted block-SELL, one lane per row => still the sequential order, bit for bit
             assert _format(gsb, Ad)["kind"] == 1 and _format(gsb, Ad)["sorted"]
             assert np.array_equal(yd.get(), yo)

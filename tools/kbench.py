@@ -1,5 +1,5 @@
 """Row-kernel micro-benchmark: achieved GB/s of every row-kernel mode on the fine-level matrices of the
-BASELINE configs.  usage: python tools/kbench.py [poisson:CELLS | elasticity:CELLS | stokes:CELLS ...] [k=v options]
+BASELINE configs.  usage: python tools/kbench.py [poisson:CELLS | elasticity:CELLS | stokes:CELLS ...] [modes=a,b] [reps=N] [k=v options]
 Reports, per mode: time, ALGORITHMIC GB/s (12 B per non-zero + per-row vector traffic) and the GB/s
 of the bytes the block-SELL format actually stores (8 + 4/bs^2 B per stored entry incl. padding)."""
 import json
@@ -24,6 +24,15 @@ def peak():
 def main():
     specs = [a for a in sys.argv[1:] if ":" in a] or ["poisson:128"]
     opts = [a.split("=", 1) for a in sys.argv[1:] if "=" in a and ":" not in a]
+    modes = ("spmv", "residual", "sweep", "spmv_dot")
+    reps = 30
+    for k, v in list(opts):  # tool arguments (not library options): modes=sweep,spmv reps=3
+        if k == "modes":
+            modes = tuple(v.split(","))
+            opts.remove([k, v])
+        elif k == "reps":
+            reps = int(v)
+            opts.remove([k, v])
     ctx = gsb.Context()
     for k, v in opts:
         ctx.set_option(k, v)
@@ -47,8 +56,8 @@ def main():
         nnz = int(rp[-1])
         fmt = A.format()
         out = {"problem": spec, "rows": n, "nnz": nnz, "format": fmt, "opts": dict(opts)}
-        for mode in ("spmv", "residual", "sweep", "spmv_dot"):
-            ms = A.bench_rows(mode, 30)
+        for mode in modes:
+            ms = A.bench_rows(mode, reps)
             gbs = (12 * nnz + PER_ROW[mode] * n) / (ms * 1e-3) / 1e9
             fgbs = (fmt["bytes_per_pass"] + PER_ROW[mode] * n - 4 * n) / (ms * 1e-3) / 1e9
             out[mode] = {"us": round(ms * 1e3, 1), "GBps_algorithmic": round(gbs, 0), "frac": round(gbs / pk, 3),
