@@ -9,6 +9,7 @@
 #include <set>
 
 #include "kernels.cuh"
+#include "sell_tma.cuh"
 #include "ops.h"
 
 namespace gsb {
@@ -429,13 +430,71 @@ static void launch_sell_inst(gsb_ctx_t ctx, const SellArgs &m, const RowArgs &a,
 #undef GSB_SELL
 }
 
+// TMA-fed persistent variant (sell_tma.cuh): CPS CTAs of WARPS warps per SM, every warp with its own three
+// shared-memory stages of KC slots; the carve-out is sized for exactly CPS CTAs so that L1 keeps what is left
+// for the gathered vector
+template <int MODE, int BS, bool PERM, int WARPS, int KC, int CPS>
+static void launch_sell_tma_cfg(gsb_ctx_t ctx, const SellArgs &m, const RowArgs &a, int64_t n_list) {
+  constexpr int smem = WARPS * 3 * SellTmaCfg<BS, KC>::STAGE_BYTES;
+  static_assert(CPS * (smem + 1024) <= 227 * 1024, "stages do not fit the shared memory of an SM");
+  auto kern = sell_tma_kernel<MODE, BS, PERM, WARPS, KC, CPS>;
+  static bool configured = false;
+  if (!configured) {
+    GSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int pct = std::min(100, (CPS * (smem + 1024) * 100) / (228 * 1024) + 1);
+    GSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    configured = true;
+  }
+  const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((n_list + WARPS - 1) / WARPS, (int64_t)CPS * ctx->num_sms));
+  kern<<<(unsigned)grid, WARPS * 32, smem, ctx->stream>>>(m, a);
+}
+template <int MODE, int BS, bool PERM>
+static void launch_sell_tma(gsb_ctx_t ctx, const SellArgs &m, const RowArgs &a, int64_t n_list, int variant) {
+  if constexpr (BS == 1) {
+    switch (variant) {
+      case 1: launch_sell_tma_cfg<MODE, 1, PERM, 4, 16, 3>(ctx, m, a, n_list); break;
+      case 2: launch_sell_tma_cfg<MODE, 1, PERM, 4, 12, 5>(ctx, m, a, n_list); break;
+      case 3: launch_sell_tma_cfg<MODE, 1, PERM, 4, 9, 6>(ctx, m, a, n_list); break;
+      case 4: launch_sell_tma_cfg<MODE, 1, PERM, 4, 8, 6>(ctx, m, a, n_list); break;
+      case 5: launch_sell_tma_cfg<MODE, 1, PERM, 4, 9, 5>(ctx, m, a, n_list); break;
+      default: launch_sell_tma_cfg<MODE, 1, PERM, 4, 16, 4>(ctx, m, a, n_list); break;
+    }
+  } else if constexpr (BS == 2) {
+    launch_sell_tma_cfg<MODE, 2, PERM, 4, 4, 4>(ctx, m, a, n_list);
+  } else {
+    launch_sell_tma_cfg<MODE, 3, PERM, 4, 3, 2>(ctx, m, a, n_list);
+  }
+}
+
+static bool use_tma(gsb_mat_t A) {
+  const std::string o = A->ctx->opt("sell_tma", "auto");
+  if (o == "0") return false;
+  if (o == "1") return true;
+  return A->bs == 1 && !A->sorted && A->n_rows >= 65536;  // auto: large scalar stencil-like matrices
+}
+
 template <int MODE>
 static void launch_sell_list(gsb_mat_t A, RowArgs &a, const int *list, int64_t n_list) {
   gsb_ctx_t ctx = A->ctx;
   if (n_list == 0 && MODE != ROW_SPMV_DOT) return;
+  if (use_tma(A)) {
+    SellArgs m{list, n_list, A->sell_perm.p, A->sell_lmask.p, A->sell_off.p, A->sell_kbase.p, A->sell_bcol.p, A->sell_val.p, A->n_brows, std::stoi(ctx->opt("debug_kernel", "0"))};
+    const int variant = std::stoi(ctx->opt("tma_variant", "0"));
+    switch (A->bs * 2 + (A->sorted ? 1 : 0)) {
+      case 2: launch_sell_tma<MODE, 1, false>(ctx, m, a, n_list, variant); break;
+      case 3: launch_sell_tma<MODE, 1, true>(ctx, m, a, n_list, variant); break;
+      case 4: launch_sell_tma<MODE, 2, false>(ctx, m, a, n_list, variant); break;
+      case 5: launch_sell_tma<MODE, 2, true>(ctx, m, a, n_list, variant); break;
+      case 6: launch_sell_tma<MODE, 3, false>(ctx, m, a, n_list, variant); break;
+      case 7: launch_sell_tma<MODE, 3, true>(ctx, m, a, n_list, variant); break;
+      default: fail(GSB_EINVAL, "block-SELL: unsupported block size");
+    }
+    launched(ctx);
+    return;
+  }
   const int64_t grid = std::max<int64_t>(1, (n_list * 32 + SELL_THREADS - 1) / SELL_THREADS);
   if (MODE == ROW_SPMV_DOT) GSB_CHECK((size_t)grid <= PARTIALS_CAP, "matrix too large for the fused dot");
-  SellArgs m{list, n_list, A->sell_perm.p, A->sell_lmask.p, A->sell_off.p, A->sell_kbase.p, A->sell_bcol.p, A->sell_val.p, A->n_brows};
+  SellArgs m{list, n_list, A->sell_perm.p, A->sell_lmask.p, A->sell_off.p, A->sell_kbase.p, A->sell_bcol.p, A->sell_val.p, A->n_brows, 0};
   const int variant = std::stoi(ctx->opt("sell_variant", "0"));
   const unsigned g = (unsigned)grid;
   switch (A->bs * 2 + (A->sorted ? 1 : 0)) {

@@ -240,6 +240,7 @@ struct SellArgs {
   const int *bcol;        // explicit block-column ids, one 32-lane line per non-affine (slice, k)
   const double *val;      // BS*BS values per block, each (k, i, j) a 32-lane line
   int64_t n_brows;        // number of block rows
+  int dbg;                // diagnostics (tools/kbench.py): bit 0 = stream the same value chunk over and over (no DRAM traffic)
 };
 
 template <int MODE, int BS, bool PERM, int THREADS, int U, int MINB>

@@ -305,6 +305,8 @@ void build_sell(gsb_mat_s *A, const int *rowptr, const int *col) {
   A->sell_bcol.alloc((size_t)std::max<int64_t>(P.n_explicit * 32, 1));
   A->sell_val.alloc((size_t)std::max<int64_t>(P.blocks, 1) * P.bs * P.bs);
   sell_fill(A, /*values_only=*/false, A->val.p);
+  if (ctx->opt("debug_zero_colwords", "0") == "1")  // diagnostics: every gather reads x[lane] (timing experiments only)
+    GSB_CUDA(cudaMemset(A->sell_kbase.p, 0, sizeof(int) * std::max<size_t>(1, P.kbase.size())));
   A->sell_ok = true;
   if (A->n_ghost_cols > 0) {
     A->n_int_slices = (int64_t)P.int_slices.size();
