@@ -9,7 +9,6 @@
 #include <set>
 
 #include "kernels.cuh"
-#include "sell_tma.cuh"
 #include "ops.h"
 
 namespace gsb {
@@ -405,105 +404,28 @@ void assemble(gsb_vec_s &v, gsb_plan_t plan) {
 // registers -- a smaller budget serialises them and loses 30 %.
 constexpr int SELL_THREADS = 256;
 template <int MODE, int BS, bool PERM>
-static void launch_sell_inst(gsb_ctx_t ctx, const SellArgs &m, const RowArgs &a, unsigned grid, int variant) {
-#define GSB_SELL(U_, MINB_) sell_kernel<MODE, BS, PERM, SELL_THREADS, U_, MINB_><<<grid, SELL_THREADS, 0, ctx->stream>>>(m, a)
-  if constexpr (BS == 1) {
-    switch (variant) {
-      case 1: GSB_SELL(9, 3); break;
-      case 2: GSB_SELL(14, 2); break;
-      case 3: GSB_SELL(9, 1); break;
-      default: GSB_SELL(9, 4); break;
-    }
-  } else if constexpr (BS == 2) {
-    switch (variant) {
-      case 1: GSB_SELL(3, 3); break;
-      case 2: GSB_SELL(6, 2); break;
-      default: GSB_SELL(4, 3); break;
-    }
-  } else {
-    switch (variant) {
-      case 1: GSB_SELL(1, 4); break;
-      case 2: GSB_SELL(3, 2); break;
-      default: GSB_SELL(2, 3); break;
-    }
-  }
-#undef GSB_SELL
-}
-
-// TMA-fed persistent variant (sell_tma.cuh): CPS CTAs of WARPS warps per SM, every warp with its own three
-// shared-memory stages of KC slots; the carve-out is sized for exactly CPS CTAs so that L1 keeps what is left
-// for the gathered vector
-template <int MODE, int BS, bool PERM, int WARPS, int KC, int CPS>
-static void launch_sell_tma_cfg(gsb_ctx_t ctx, const SellArgs &m, const RowArgs &a, int64_t n_list) {
-  constexpr int smem = WARPS * 3 * SellTmaCfg<BS, KC>::STAGE_BYTES;
-  static_assert(CPS * (smem + 1024) <= 227 * 1024, "stages do not fit the shared memory of an SM");
-  auto kern = sell_tma_kernel<MODE, BS, PERM, WARPS, KC, CPS>;
-  static bool configured = false;
-  if (!configured) {
-    GSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int pct = std::min(100, (CPS * (smem + 1024) * 100) / (228 * 1024) + 1);
-    GSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-    configured = true;
-  }
-  const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((n_list + WARPS - 1) / WARPS, (int64_t)CPS * ctx->num_sms));
-  kern<<<(unsigned)grid, WARPS * 32, smem, ctx->stream>>>(m, a);
-}
-template <int MODE, int BS, bool PERM>
-static void launch_sell_tma(gsb_ctx_t ctx, const SellArgs &m, const RowArgs &a, int64_t n_list, int variant) {
-  if constexpr (BS == 1) {
-    switch (variant) {
-      case 1: launch_sell_tma_cfg<MODE, 1, PERM, 4, 16, 3>(ctx, m, a, n_list); break;
-      case 2: launch_sell_tma_cfg<MODE, 1, PERM, 4, 12, 5>(ctx, m, a, n_list); break;
-      case 3: launch_sell_tma_cfg<MODE, 1, PERM, 4, 9, 6>(ctx, m, a, n_list); break;
-      case 4: launch_sell_tma_cfg<MODE, 1, PERM, 4, 8, 6>(ctx, m, a, n_list); break;
-      case 5: launch_sell_tma_cfg<MODE, 1, PERM, 4, 9, 5>(ctx, m, a, n_list); break;
-      default: launch_sell_tma_cfg<MODE, 1, PERM, 4, 16, 4>(ctx, m, a, n_list); break;
-    }
-  } else if constexpr (BS == 2) {
-    launch_sell_tma_cfg<MODE, 2, PERM, 4, 4, 4>(ctx, m, a, n_list);
-  } else {
-    launch_sell_tma_cfg<MODE, 3, PERM, 4, 3, 2>(ctx, m, a, n_list);
-  }
-}
-
-static bool use_tma(gsb_mat_t A) {
-  const std::string o = A->ctx->opt("sell_tma", "auto");
-  if (o == "0") return false;
-  if (o == "1") return true;
-  return A->bs == 1 && !A->sorted && A->n_rows >= 65536;  // auto: large scalar stencil-like matrices
+static void launch_sell_inst(gsb_ctx_t ctx, const SellArgs &m, const RowArgs &a, unsigned grid) {
+  // (unroll depth, CTAs per SM): 9 scalar entries / 4 2x2 blocks / 2 3x3 blocks in flight per lane
+  if constexpr (BS == 1) sell_kernel<MODE, 1, PERM, SELL_THREADS, 9, 4><<<grid, SELL_THREADS, 0, ctx->stream>>>(m, a);
+  else if constexpr (BS == 2) sell_kernel<MODE, 2, PERM, SELL_THREADS, 4, 3><<<grid, SELL_THREADS, 0, ctx->stream>>>(m, a);
+  else sell_kernel<MODE, 3, PERM, SELL_THREADS, 2, 3><<<grid, SELL_THREADS, 0, ctx->stream>>>(m, a);
 }
 
 template <int MODE>
 static void launch_sell_list(gsb_mat_t A, RowArgs &a, const int *list, int64_t n_list) {
   gsb_ctx_t ctx = A->ctx;
   if (n_list == 0 && MODE != ROW_SPMV_DOT) return;
-  if (use_tma(A)) {
-    SellArgs m{list, n_list, A->sell_perm.p, A->sell_lmask.p, A->sell_off.p, A->sell_kbase.p, A->sell_bcol.p, A->sell_val.p, A->n_brows, std::stoi(ctx->opt("debug_kernel", "0"))};
-    const int variant = std::stoi(ctx->opt("tma_variant", "0"));
-    switch (A->bs * 2 + (A->sorted ? 1 : 0)) {
-      case 2: launch_sell_tma<MODE, 1, false>(ctx, m, a, n_list, variant); break;
-      case 3: launch_sell_tma<MODE, 1, true>(ctx, m, a, n_list, variant); break;
-      case 4: launch_sell_tma<MODE, 2, false>(ctx, m, a, n_list, variant); break;
-      case 5: launch_sell_tma<MODE, 2, true>(ctx, m, a, n_list, variant); break;
-      case 6: launch_sell_tma<MODE, 3, false>(ctx, m, a, n_list, variant); break;
-      case 7: launch_sell_tma<MODE, 3, true>(ctx, m, a, n_list, variant); break;
-      default: fail(GSB_EINVAL, "block-SELL: unsupported block size");
-    }
-    launched(ctx);
-    return;
-  }
   const int64_t grid = std::max<int64_t>(1, (n_list * 32 + SELL_THREADS - 1) / SELL_THREADS);
   if (MODE == ROW_SPMV_DOT) GSB_CHECK((size_t)grid <= PARTIALS_CAP, "matrix too large for the fused dot");
-  SellArgs m{list, n_list, A->sell_perm.p, A->sell_lmask.p, A->sell_off.p, A->sell_kbase.p, A->sell_bcol.p, A->sell_val.p, A->n_brows, 0};
-  const int variant = std::stoi(ctx->opt("sell_variant", "0"));
+  SellArgs m{list, n_list, A->sell_perm.p, A->sell_lmask.p, A->sell_off.p, A->sell_kbase.p, A->sell_bcol.p, A->sell_val.p, A->n_brows, A->sell_kind.p, A->n_own_cols + A->n_ghost_cols};
   const unsigned g = (unsigned)grid;
   switch (A->bs * 2 + (A->sorted ? 1 : 0)) {
-    case 2: launch_sell_inst<MODE, 1, false>(ctx, m, a, g, variant); break;
-    case 3: launch_sell_inst<MODE, 1, true>(ctx, m, a, g, variant); break;
-    case 4: launch_sell_inst<MODE, 2, false>(ctx, m, a, g, variant); break;
-    case 5: launch_sell_inst<MODE, 2, true>(ctx, m, a, g, variant); break;
-    case 6: launch_sell_inst<MODE, 3, false>(ctx, m, a, g, variant); break;
-    case 7: launch_sell_inst<MODE, 3, true>(ctx, m, a, g, variant); break;
+    case 2: launch_sell_inst<MODE, 1, false>(ctx, m, a, g); break;
+    case 3: launch_sell_inst<MODE, 1, true>(ctx, m, a, g); break;
+    case 4: launch_sell_inst<MODE, 2, false>(ctx, m, a, g); break;
+    case 5: launch_sell_inst<MODE, 2, true>(ctx, m, a, g); break;
+    case 6: launch_sell_inst<MODE, 3, false>(ctx, m, a, g); break;
+    case 7: launch_sell_inst<MODE, 3, true>(ctx, m, a, g); break;
     default: fail(GSB_EINVAL, "block-SELL: unsupported block size");
   }
   launched(ctx);
@@ -849,10 +771,10 @@ int gsb_init(int device, int nranks, int rank, const void *nccl_id, gsb_ctx_t *o
   GSB_CUDA(cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming));
   GSB_CUDA(cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming));
   ctx->scal.alloc(65536);
-  GSB_CUDA(cudaMemset(ctx->scal.p, 0, sizeof(double) * ctx->scal.n));
+  GSB_CUDA(cudaMemsetAsync(ctx->scal.p, 0, sizeof(double) * ctx->scal.n, ctx->stream));
   ctx->partials.alloc(PARTIALS_CAP);
   ctx->ticket.alloc(4);
-  GSB_CUDA(cudaMemset(ctx->ticket.p, 0, sizeof(unsigned int) * 4));
+  GSB_CUDA(cudaMemsetAsync(ctx->ticket.p, 0, sizeof(unsigned int) * 4, ctx->stream));
   GSB_CUDA(cudaMallocHost(&ctx->h_scal, sizeof(double) * (gsb_ctx_s::H_SCAL_READ + 8)));
   if (nranks > 1) {
     GSB_CHECK(nccl_id != nullptr, "gsb_init: nccl id required for nranks > 1");
@@ -957,7 +879,8 @@ int gsb_bench_rows(gsb_mat_t A, int mode, int reps, float *avg_ms) {
     GSB_CUDA(cudaMalloc(&p->d, sizeof(double) * std::max<int64_t>(1, n_own + n_ghost)));
     std::vector<double> h((size_t)(n_own + n_ghost));
     for (size_t i = 0; i < h.size(); ++i) h[i] = v * std::sin((double)i);
-    GSB_CUDA(cudaMemcpy(p->d, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice));
+    GSB_CUDA(cudaMemcpyAsync(p->d, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, ctx->stream));
+    GSB_CUDA(cudaStreamSynchronize(ctx->stream));
     return p;
   };
   auto x = mk(A->n_own_cols, A->n_ghost_cols, 1.0), x2 = mk(A->n_own_cols, A->n_ghost_cols, 1.0);
@@ -1010,6 +933,8 @@ static void release_p2p(gsb_plan_s *p) {
   p->p2p = false;
 }
 
+// (set-up only) copies issued on the legacy stream are not ordered with the context's non-blocking streams: a
+// pageable cudaMemcpy returns once the data is staged, so each of them is followed by a device-wide synchronisation
 static void setup_p2p(gsb_plan_s *p) {
   gsb_ctx_t ctx = p->ctx;
   const int R = ctx->nranks, me = ctx->rank;
@@ -1019,7 +944,7 @@ static void setup_p2p(gsb_plan_s *p) {
   const size_t bytes = p->flag_bytes + 2 * sizeof(double) * (size_t)std::max<int64_t>(nrcv, 1);
   cudaIpcMemHandle_t h;
   std::memset(&h, 0, sizeof(h));
-  if (cudaMalloc(&p->block, bytes) != cudaSuccess || cudaMemset(p->block, 0, bytes) != cudaSuccess ||
+  if (cudaMalloc(&p->block, bytes) != cudaSuccess || cudaMemset(p->block, 0, bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
       cudaIpcGetMemHandle(&h, p->block) != cudaSuccess) {
     ok = 0.0;
     (void)cudaGetLastError();
@@ -1034,6 +959,7 @@ static void setup_p2p(gsb_plan_s *p) {
   for (size_t k = 0; k < p->nbr_rcv.size(); ++k) meta[1 + p->nbr_rcv[k]] = p->rcv_ptrs[k];
   DevBuf<char> dmine(rec), dall(rec * (size_t)R);
   GSB_CUDA(cudaMemcpy(dmine.p, mine.data(), rec, cudaMemcpyHostToDevice));
+  GSB_CUDA(cudaDeviceSynchronize());
   GSB_NCCL(ncclAllGather(dmine.p, dall.p, rec, ncclChar, ctx->comm, ctx->stream));
   GSB_CUDA(cudaStreamSynchronize(ctx->stream));
   GSB_CUDA(cudaMemcpy(all.data(), dall.p, all.size(), cudaMemcpyDeviceToHost));
@@ -1066,6 +992,7 @@ static void setup_p2p(gsb_plan_s *p) {
   // mapped its peers): sum of the per-rank ok flags must be R
   DevBuf<double> tok(1);
   GSB_CUDA(cudaMemcpy(tok.p, &ok, sizeof(double), cudaMemcpyHostToDevice));
+  GSB_CUDA(cudaDeviceSynchronize());
   GSB_NCCL(ncclAllReduce(tok.p, tok.p, 1, ncclDouble, ncclSum, ctx->comm, ctx->stream));
   double total = 0.0;
   GSB_CUDA(cudaMemcpyAsync(&total, tok.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1078,22 +1005,30 @@ static void setup_p2p(gsb_plan_s *p) {
   p->peer_buf[1].alloc(pb1.size());
   p->peer_flag.alloc(pf.size());
   GSB_CUDA(cudaMemcpy(p->peer_buf[0].p, pb0.data(), sizeof(double *) * pb0.size(), cudaMemcpyHostToDevice));
+  GSB_CUDA(cudaDeviceSynchronize());
   GSB_CUDA(cudaMemcpy(p->peer_buf[1].p, pb1.data(), sizeof(double *) * pb1.size(), cudaMemcpyHostToDevice));
+  GSB_CUDA(cudaDeviceSynchronize());
   GSB_CUDA(cudaMemcpy(p->peer_flag.p, pf.data(), sizeof(unsigned long long *) * pf.size(), cudaMemcpyHostToDevice));
+  GSB_CUDA(cudaDeviceSynchronize());
   std::vector<int> snbr((size_t)std::max<int64_t>(nsnd, 1), 0);
   for (size_t k = 0; k < nn; ++k)
     for (int64_t i = p->snd_ptrs[k]; i < p->snd_ptrs[k + 1]; ++i) snbr[(size_t)i] = (int)k;
   p->snd_nbr.alloc(snbr.size());
   GSB_CUDA(cudaMemcpy(p->snd_nbr.p, snbr.data(), sizeof(int) * snbr.size(), cudaMemcpyHostToDevice));
+  GSB_CUDA(cudaDeviceSynchronize());
   p->snd_ptrs_dev.alloc(p->snd_ptrs.size());
   GSB_CUDA(cudaMemcpy(p->snd_ptrs_dev.p, p->snd_ptrs.data(), sizeof(int64_t) * p->snd_ptrs.size(), cudaMemcpyHostToDevice));
+  GSB_CUDA(cudaDeviceSynchronize());
   p->nbr_rcv_dev.alloc(std::max<size_t>(1, p->nbr_rcv.size()));
   if (!p->nbr_rcv.empty())
     GSB_CUDA(cudaMemcpy(p->nbr_rcv_dev.p, p->nbr_rcv.data(), sizeof(int) * p->nbr_rcv.size(), cudaMemcpyHostToDevice));
+  GSB_CUDA(cudaDeviceSynchronize());
   p->ticket.alloc(1);
   GSB_CUDA(cudaMemset(p->ticket.p, 0, sizeof(unsigned int)));
+  GSB_CUDA(cudaDeviceSynchronize());
   p->seq_dev.alloc(1);
   GSB_CUDA(cudaMemset(p->seq_dev.p, 0, sizeof(unsigned long long)));
+  GSB_CUDA(cudaDeviceSynchronize());
   // second barrier: every rank's counters are initialised before anybody's first exchange
   GSB_NCCL(ncclAllReduce(tok.p, tok.p, 1, ncclDouble, ncclSum, ctx->comm, ctx->stream));
   GSB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1131,7 +1066,9 @@ int gsb_plan_create(gsb_ctx_t ctx, int64_t n_own, int64_t n_ghost, int n_nbr_snd
   p->snd_buf.alloc(std::max<size_t>(1, s.size()));
   p->rcv_buf.alloc(std::max<size_t>(1, r.size()));
   if (nsnd) GSB_CUDA(cudaMemcpy(p->snd_ids.p, s.data(), sizeof(int) * s.size(), cudaMemcpyHostToDevice));
+  GSB_CUDA(cudaDeviceSynchronize());
   if (nrcv) GSB_CUDA(cudaMemcpy(p->rcv_ids.p, r.data(), sizeof(int) * r.size(), cudaMemcpyHostToDevice));
+  GSB_CUDA(cudaDeviceSynchronize());
   if (ctx->nranks > 1 && ctx->opt("p2p", "1") == "1") setup_p2p(p.get());
   if (ctx->nranks > 1 && !p->p2p) ctx->nccl_halo_in_use = true;
   *out = p.release();

@@ -162,7 +162,7 @@ struct gsb_mat_s {
   int64_t sell_blocks = 0;  // stored blocks incl. padding
   int64_t sell_explicit = 0;  // (slice, k) pairs whose 32 block-column ids are stored explicitly (the others are affine)
   int64_t sell_aligned = 0;   // diagonal-aligned slices (all their column words are affine)
-  gsb::DevBuf<int> sell_perm, sell_lmask, sell_off, sell_kbase, sell_bcol;
+  gsb::DevBuf<int> sell_perm, sell_lmask, sell_off, sell_kbase, sell_kind, sell_bcol;
   gsb::DevBuf<double> sell_val;
   // halo overlap: slices whose rows touch no ghost column ("interior") run while the exchange is in
   // flight, the remaining ("boundary") slices after it

@@ -240,7 +240,8 @@ struct SellArgs {
   const int *bcol;        // explicit block-column ids, one 32-lane line per non-affine (slice, k)
   const double *val;      // BS*BS values per block, each (k, i, j) a 32-lane line
   int64_t n_brows;        // number of block rows
-  int dbg;                // diagnostics (tools/kbench.py): bit 0 = stream the same value chunk over and over (no DRAM traffic)
+  const int *kind;        // per slice: 1 = diagonal-aligned slice whose slots come in runs of three consecutive columns
+  int64_t n_cols;         // entries of the gathered vector (own + ghost columns)
 };
 
 template <int MODE, int BS, bool PERM, int THREADS, int U, int MINB>
@@ -280,6 +281,57 @@ __global__ void __launch_bounds__(THREADS, MINB) sell_kernel(SellArgs m, RowArgs
     const double *vp = m.val + (((size_t)so0 * BB) << 5) + lane;
     const double al = a.alpha;
     int k = 0;
+    if (BS == 1 && !PERM && m.kind[slice] == 1) {
+      // Slots in runs of three consecutive columns (c, c+1, c+2: the x-neighbours of a stencil).  The three
+      // gathers of a run read the 34 entries x[c .. c+33]: ONE full-width gather (lane l: x[c+l]) plus one
+      // two-lane gather (x[c+32], x[c+33]); the shifted operands come from warp shuffles.  A third of the L1
+      // requests of the generic loop; the values, their order and every rounding are unchanged.
+      const int nt = width / 3;
+      auto run3 = [&](int t, const double (&v)[3], double M, double E) {
+        const double d1 = __shfl_down_sync(0xffffffffu, M, 1), d2 = __shfl_down_sync(0xffffffffu, M, 2);
+        const double e0 = __shfl_sync(0xffffffffu, E, 0), e1 = __shfl_sync(0xffffffffu, E, 1);
+        double xs[3];
+        xs[0] = M;
+        xs[1] = lane == 31 ? e0 : d1;
+        xs[2] = lane == 30 ? e0 : (lane == 31 ? e1 : d2);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          if (slot_on(3 * t + j)) {
+            const double xj = (MODE == ROW_SPMV) ? __dmul_rn(xs[j], al) : xs[j];
+            s[0] = __dadd_rn(s[0], __dmul_rn(v[j], xj));
+          }
+        }
+      };
+      auto gather3 = [&](int kb, double &M, double &E) {
+        const int c = kb + lane;
+        M = ((unsigned)c < (unsigned)m.n_cols) ? ldg_nc_f64(a.x + c) : 0.0;
+        E = (lane < 2 && (unsigned)(c + 32) < (unsigned)m.n_cols) ? ldg_nc_f64(a.x + c + 32) : 0.0;
+      };
+      int t = 0;
+      for (; t + 3 <= nt; t += 3) {
+        int kb[3];
+        double vv[3][3], M[3], E[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) kb[q] = ldg_nc_s32(kp + 3 * (t + q));
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) vv[q][j] = ldg_stream_f64(vp + (size_t)(3 * (t + q) + j) * 32);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) gather3(kb[q], M[q], E[q]);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) run3(t + q, vv[q], M[q], E[q]);
+      }
+      for (; t < nt; ++t) {
+        double vv[3], M, E;
+        const int kb = ldg_nc_s32(kp + 3 * t);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) vv[j] = ldg_stream_f64(vp + (size_t)(3 * t + j) * 32);
+        gather3(kb, M, E);
+        run3(t, vv, M, E);
+      }
+      k = width;  // nothing left for the generic loops
+    }
     for (; k + U <= width; k += U) {
       int cc[U];
       double vv[U][BB], xv[U][BS];

@@ -86,11 +86,13 @@ struct SellPlan {
   std::vector<int> perm, blen, off;      // perm empty when !sorted; blen by position (blocks per block row), padded with 0
   std::vector<int> lmask;                // per position: validity word of its slots (bit mask, or length when width > 32)
   std::vector<int> kbase;                // per (slice, k): affine base block column, or ~(explicit line)
+  std::vector<int> kind;                 // per slice: 1 = aligned slice made of runs of three consecutive columns
+  int64_t triple_slices = 0;
   std::vector<int> int_slices, bnd_slices;
 };
 
 SellPlan plan_sell(int64_t n_rows, int64_t n_own_cols, int64_t n_ghost_cols, const int *rowptr, const int *col, bool detect_blocks,
-                   const std::string &sort_opt, bool affine = true, bool dia = true) {
+                   const std::string &sort_opt, bool affine = true, bool dia = true, bool triples = true) {
   SellPlan P;
   if (n_rows == 0) return P;
   const int64_t n_cols = n_own_cols + n_ghost_cols;
@@ -255,6 +257,22 @@ SellPlan plan_sell(int64_t n_rows, int64_t n_own_cols, int64_t n_ghost_cols, con
     P.n_explicit = nexp;
     P.aligned_slices = 0;
     for (int64_t sl = 0; sl < nsl; ++sl) P.aligned_slices += aligned[(size_t)sl];
+    // aligned slices whose slots come in runs of three consecutive columns (stencil x-neighbours) and have no
+    // explicit line: the kernel gathers every run once and shuffles (kernels.cuh, sell_kernel)
+    P.kind.assign((size_t)nsl, 0);
+    if (BS == 1 && triples) {
+      int64_t ntri = 0;
+#pragma omp parallel for schedule(static) reduction(+ : ntri)
+      for (int64_t sl = 0; sl < nsl; ++sl) {
+        if (!aligned[(size_t)sl]) continue;
+        const int w = width[(size_t)sl];
+        const int *kb = P.kbase.data() + P.off[(size_t)sl];
+        bool ok = w > 0 && w % 3 == 0;
+        for (int k = 0; k < w && ok; k += 3) ok = kb[k] >= 0 && kb[k + 1] == kb[k] + 1 && kb[k + 2] == kb[k] + 2;
+        if (ok) { P.kind[(size_t)sl] = 1; ntri += 1; }
+      }
+      P.triple_slices = ntri;
+    }
   }
   // interior / boundary slice lists (only for matrices with ghost columns): a slice is "boundary" when one
   // of its block rows references a ghost column (columns ascend: the last one decides)
@@ -285,7 +303,7 @@ void build_sell(gsb_mat_s *A, const int *rowptr, const int *col) {
   A->split_ok = false;
   if (A->n_rows == 0 || ctx->opt("sell", "1") != "1") return;
   SellPlan P = plan_sell(A->n_rows, A->n_own_cols, A->n_ghost_cols, rowptr, col, ctx->opt("block", "1") == "1",
-                         ctx->opt("sell_sort", "auto"), ctx->opt("sell_affine", "1") == "1", ctx->opt("sell_align", "1") == "1");
+                         ctx->opt("sell_sort", "auto"), ctx->opt("sell_affine", "1") == "1", ctx->opt("sell_align", "1") == "1", ctx->opt("sell_triples", "1") == "1");
   if (!P.ok) return;
   A->bs = P.bs;
   A->sorted = P.sorted;
@@ -296,17 +314,16 @@ void build_sell(gsb_mat_s *A, const int *rowptr, const int *col) {
   A->sell_aligned = P.aligned_slices;
   auto up = [&](DevBuf<int> &d, const std::vector<int> &h) {
     d.alloc(std::max<size_t>(1, h.size()));
-    if (!h.empty()) GSB_CUDA(cudaMemcpy(d.p, h.data(), sizeof(int) * h.size(), cudaMemcpyHostToDevice));
+    if (!h.empty()) GSB_CUDA(cudaMemcpyAsync(d.p, h.data(), sizeof(int) * h.size(), cudaMemcpyHostToDevice, ctx->stream));
   };
   up(A->sell_lmask, P.lmask);
   up(A->sell_off, P.off);
   if (P.sorted) up(A->sell_perm, P.perm);
   up(A->sell_kbase, P.kbase);
+  up(A->sell_kind, P.kind);
   A->sell_bcol.alloc((size_t)std::max<int64_t>(P.n_explicit * 32, 1));
   A->sell_val.alloc((size_t)std::max<int64_t>(P.blocks, 1) * P.bs * P.bs);
   sell_fill(A, /*values_only=*/false, A->val.p);
-  if (ctx->opt("debug_zero_colwords", "0") == "1")  // diagnostics: every gather reads x[lane] (timing experiments only)
-    GSB_CUDA(cudaMemset(A->sell_kbase.p, 0, sizeof(int) * std::max<size_t>(1, P.kbase.size())));
   A->sell_ok = true;
   if (A->n_ghost_cols > 0) {
     A->n_int_slices = (int64_t)P.int_slices.size();
@@ -315,6 +332,7 @@ void build_sell(gsb_mat_s *A, const int *rowptr, const int *col) {
     up(A->bnd_slices, P.bnd_slices);
     A->split_ok = true;
   }
+  GSB_CUDA(cudaStreamSynchronize(ctx->stream));  // the plan's host arrays go out of scope here
 }
 
 // rowptr/col/val: CSR with int32 0-based ascending columns (host; may be the caller's own buffers)
@@ -325,10 +343,12 @@ void finish_matrix(gsb_mat_s *A, const int *rowptr, const int *col, const double
   A->rowptr.alloc((size_t)A->n_rows + 1);
   A->col.alloc(nnz_alloc);
   A->val.alloc(nnz_alloc);
-  GSB_CUDA(cudaMemcpy(A->rowptr.p, rowptr, sizeof(int) * ((size_t)A->n_rows + 1), cudaMemcpyHostToDevice));
+  // uploads go through the context's (non-blocking) stream: a plain cudaMemcpy from pageable memory returns once
+  // the data is staged, its DMA is ordered in the legacy stream only and would race with the kernels below
+  GSB_CUDA(cudaMemcpyAsync(A->rowptr.p, rowptr, sizeof(int) * ((size_t)A->n_rows + 1), cudaMemcpyHostToDevice, ctx->stream));
   if (A->nnz) {
-    GSB_CUDA(cudaMemcpy(A->col.p, col, sizeof(int) * (size_t)A->nnz, cudaMemcpyHostToDevice));
-    GSB_CUDA(cudaMemcpy(A->val.p, val, sizeof(double) * (size_t)A->nnz, cudaMemcpyHostToDevice));
+    GSB_CUDA(cudaMemcpyAsync(A->col.p, col, sizeof(int) * (size_t)A->nnz, cudaMemcpyHostToDevice, ctx->stream));
+    GSB_CUDA(cudaMemcpyAsync(A->val.p, val, sizeof(double) * (size_t)A->nnz, cudaMemcpyHostToDevice, ctx->stream));
   }
   A->csr_kept = true;
   int mx = 0;
@@ -342,8 +362,8 @@ void finish_matrix(gsb_mat_s *A, const int *rowptr, const int *col, const double
   build_sell(A, rowptr, col);
   // large matrices stream the block-SELL arrays only: release the CSR column ids / values
   const int64_t keep_max = std::stoll(ctx->opt("keep_csr_max_nnz", "16777216"));
+  GSB_CUDA(cudaStreamSynchronize(ctx->stream));  // the caller's / the converter's host arrays may go away now
   if (A->sell_ok && A->nnz > keep_max && ctx->opt("keep_csr", "0") != "1") {
-    GSB_CUDA(cudaStreamSynchronize(ctx->stream));
     A->col.release();
     A->val.release();
     A->csr_kept = false;
@@ -505,7 +525,7 @@ int gsb_mat_destroy(gsb_mat_t A) {
 // diagnostics (pure host, no device needed): the block-SELL plan the library would build for a CSR matrix
 // (int32, 0-based, ascending columns).  out[12] = {ok, block size, sorted, block rows, slices, stored blocks incl.
 // padding, blocks without padding, boundary slices, explicit (slice,k) id lines, (slice,k) pairs, diagonal-aligned
-// slices, 0}; pos_row (n_slices*32 ints or NULL) receives the block row of every (slice, lane) position (-1 =
+// slices, slices made of runs of three consecutive columns}; pos_row (n_slices*32 ints or NULL) receives the block row of every (slice, lane) position (-1 =
 // padding lane), pos_len its length in blocks, pos_mask its slot-validity word, col_words (out[9] ints or NULL) the
 // column word of every (slice, k) pair (>= 0: affine base)
 int gsb_diag_sell_plan(int64_t n_rows, int64_t n_own_cols, int64_t n_ghost_cols, const int *rowptr, const int *col,
@@ -516,7 +536,7 @@ int gsb_diag_sell_plan(int64_t n_rows, int64_t n_own_cols, int64_t n_ghost_cols,
                          sort_mode < 0 ? "auto" : (sort_mode ? "1" : "0"));
   out[0] = P.ok; out[1] = P.bs; out[2] = P.sorted; out[3] = P.n_brows; out[4] = P.n_slices; out[5] = P.blocks;
   out[6] = P.sum_blocks; out[7] = (int64_t)P.bnd_slices.size(); out[8] = P.n_explicit; out[9] = (int64_t)P.kbase.size();
-  out[10] = P.aligned_slices; out[11] = 0;
+  out[10] = P.aligned_slices; out[11] = P.triple_slices;
   if (P.ok) {
     if (col_words) std::copy(P.kbase.begin(), P.kbase.end(), col_words);
     for (int64_t pos = 0; pos < P.n_slices * 32; ++pos) {

@@ -70,7 +70,7 @@ int gsb_profile_stop(gsb_ctx_t ctx, int cap, int *n_out, int *mode, int *stream_
                      int *count, double *total_ms);
 /* diagnostics (pure host): the block-SELL-32 plan the library builds for a CSR matrix (int32, 0-based, ascending
  * columns): out[12] = {ok, block size, sorted, block rows, slices, stored blocks incl. padding, blocks without
- * padding, boundary slices, explicit column-id lines, (slice,k) pairs, diagonal-aligned slices, 0}; pos_row / pos_len
+ * padding, boundary slices, explicit column-id lines, (slice,k) pairs, diagonal-aligned slices, slices made of runs of three consecutive columns}; pos_row / pos_len
  * / pos_mask (n_slices*32 ints or NULL): block row (-1 = padding lane), length in blocks and slot-validity word (slice
  * width <= 32: bit k set <=> slot k holds a block; else the length) of every (slice, lane) position; col_words (one
  * int per (slice,k) pair = stored blocks / 32, or NULL): >= 0 the affine base block column (lane l uses base + l),

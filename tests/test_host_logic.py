@@ -342,7 +342,7 @@ def _sell_plan(A, n_ghost=0, blocks=1, sort=-1):
                                               out.ctypes.data, prow.ctypes.data, plen.ctypes.data, pmask.ctypes.data, words.ctypes.data)
     assert rc == 0
     keys = ("ok", "bs", "sorted", "n_brows", "n_slices", "blocks", "sum_blocks", "bnd_slices", "explicit_lines", "pairs",
-            "aligned_slices")
+            "aligned_slices", "triple_slices")
     d = dict(zip(keys, (int(v) for v in out)))
     d["col_words"] = words[: d["pairs"]].copy()
     d["col"] = col
@@ -408,6 +408,10 @@ def test_sell_plan_scalar_q1_is_unsorted_and_tight():
     # that cross mesh-line ends (the first slices keep explicit lines for the slots that reach before column 0)
     assert d["aligned_slices"] >= 0.95 * d["n_slices"]
     assert _check_col_words(d, prow, plen, rp) > 0.9
+    # the x-neighbours (c-1, c, c+1) of the 27-point stencil: slots in runs of three consecutive columns
+    assert d["triple_slices"] >= 0.9 * d["n_slices"]
+    w = d["col_words"]
+    assert d["pairs"] % 3 == 0 or d["triple_slices"] < d["n_slices"]
     # without alignment the padding is a little smaller and a good part of the words is explicit
     assert d["blocks"] <= 1.06 * d["sum_blocks"]
 

@@ -1,3 +1,13 @@
+// EXPERIMENT, NOT PART OF THE BUILD (round 2).  Kept for the record next to profiles/sell_tma_r02.json:
+// a TMA-fed persistent variant of the block-SELL kernel.  Findings on B200 (C2 fine level, 2 048 383 rows):
+//   * with the gathers of x made trivial (all column words 0) the bulk-copy value stream runs at 1.005 of the
+//     measured HBM copy peak (SpMV 73.9 us for 454 MB) -- the register-fed kernel reaches 0.84 in the same test;
+//   * with the real gathers every variant (2/3 stages, 16..24 warps per SM, gathers software-pipelined one chunk
+//     ahead, x windows staged in shared memory with LDGSTS) lands at 94..100 us: the kernel is bound by the NUMBER
+//     of L1 gather requests (T ~= 0.074 us/MB + 31 us per million warp-gathers), not by bytes in flight;
+//   * the fix that paid is in the format / register kernel instead: runs of three consecutive columns are gathered
+//     once and shuffled (kernels.cuh sell_kernel, `kind` slices): SpMV 78.8 us, residual 79.8 us, sweep 95.2 us.
+// To try it again: copy next to kernels.cuh, include from core.cu and dispatch from launch_sell_list.
 // sell_tma.cuh -- TMA-fed persistent variant of the block-SELL-32 row kernel (kernels.cuh sell_kernel).
 //
 // Why: with the column ids compressed to one word per 32 blocks (diagonal-aligned slices) the register-fed
