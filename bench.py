@@ -122,18 +122,20 @@ class ClockSampler:
 # the same constructor sequence builds the device solver (S = gsb200) and the CPU restatement (S = oracle.solvers)
 
 
-def gmg_stack(S, mats, P, R, nlev, **kw):
+def gmg_stack(S, mats, P, R, nlev, redist=None, **kw):
     sm = [S.RichardsonSmoother(S.JacobiLinearSolver(), 10, 2.0 / 3.0)] * (nlev - 1)
+    if redist is not None:  # device side only: coarse levels on fewer parts
+        kw["redist"] = redist
     return S.GMGLinearSolver(mats, P, R, pre_smoothers=sm, post_smoothers=sm, coarsest_solver=S.LUSolver(), **kw)
 
 
-def c2_solver(S, mats, P, R, nlev, maxiter=MAXITER):
-    gmg = gmg_stack(S, mats, P, R, nlev, maxiter=1, mode="preconditioner", cycle_type="v_cycle")
+def c2_solver(S, mats, P, R, nlev, maxiter=MAXITER, redist=None):
+    gmg = gmg_stack(S, mats, P, R, nlev, redist=redist, maxiter=1, mode="preconditioner", cycle_type="v_cycle")
     return S.CGSolver(gmg, maxiter=maxiter, atol=ATOL, rtol=RTOL)
 
 
-def c4_solver(S, mats, P, R, nlev, maxiter=MAXITER):
-    gmg = gmg_stack(S, mats, P, R, nlev, maxiter=1, mode="preconditioner", cycle_type="v_cycle")
+def c4_solver(S, mats, P, R, nlev, maxiter=MAXITER, redist=None):
+    gmg = gmg_stack(S, mats, P, R, nlev, redist=redist, maxiter=1, mode="preconditioner", cycle_type="v_cycle")
     return S.FGMRESSolver(30, gmg, maxiter=maxiter, atol=ATOL, rtol=RTOL)
 
 
@@ -158,7 +160,7 @@ def oracle_mats(hh_A, hh_P, hh_R, ns_own):
 class Problem:
     """host data of one configuration + builders of the device and the oracle solver"""
 
-    def __init__(self, config, cells, parts=(1, 1, 1), rank=0, serial_of=None):
+    def __init__(self, config, cells, parts=(1, 1, 1), rank=0, serial_of=None, agglomerate_rows=0):
         """serial_of=(px,py,pz): the SERIAL system with the global mesh of that part grid (the oracle side of the
         multi-GPU parity check)"""
         from gsb200 import synth
@@ -170,7 +172,18 @@ class Problem:
             nranks = int(np.prod(grid))
             self.nlev = 4 if (nranks == 1 and cells == 128) else n_levels(cells)
             self.ncell = tuple(cells * p for p in grid)
-            self.hh = synth.poisson_hierarchy_host(self.ncell, self.nlev, parts=parts, rank=rank, lengths=tuple(float(p) for p in grid))
+            # levels with at most `agglomerate_rows` rows per part live on rank 0 only (the reference's np_per_level):
+            # no halo exchange below that level, one redistribution on the way down and one on the way up
+            ppl = None
+            if agglomerate_rows > 0 and int(np.prod(parts)) > 1:
+                ppl = [tuple(parts) if (cells >> l) ** 3 > agglomerate_rows else (1, 1, 1) for l in range(self.nlev)]
+                ppl[0] = tuple(parts)
+                for l in range(1, self.nlev):  # monotone: once on one part, always on one part
+                    if ppl[l - 1] == (1, 1, 1):
+                        ppl[l] = (1, 1, 1)
+            self.parts_per_level = ppl
+            self.hh = synth.poisson_hierarchy_host(self.ncell, self.nlev, parts=parts, rank=rank, lengths=tuple(float(p) for p in grid),
+                                                   parts_per_level=ppl)
             self.n_own = self.hh.levels[0].n_own
             self.n_glob = int(np.prod([c - 1 for c in self.ncell]))
             self.b = self.hh.b
@@ -216,7 +229,7 @@ class Problem:
         if self.config in ("c2", "c4"):
             dh = synth.upload_hierarchy(ctx, self.hh)
             self.dh = dh
-            solver = (c2_solver if self.config == "c2" else c4_solver)(gsb, dh.A, dh.P, dh.R, self.nlev)
+            solver = (c2_solver if self.config == "c2" else c4_solver)(gsb, dh.A, dh.P, dh.R, self.nlev, redist=dh.redist)
             A = dh.A[0]
             self.fine = dh.A[0]
             self.level_rows = [lp.n_own for lp in self.hh.levels]
@@ -348,6 +361,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scaling-base", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--agglomerate-rows", type=int, default=int(os.environ.get("GSB_BENCH_AGGLOMERATE_ROWS", "5000")),
+                    help="N>1: GMG levels with at most this many rows per GPU live on rank 0 only (0 = every level on every GPU)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -392,7 +407,8 @@ def main():
     def measure(config, cells, steps, warmup, c=None, parts=None, with_e2e=True, with_profile=True, distributed=True):
         c = c or ctx
         parts = parts or (PARTS[world] if distributed else (1, 1, 1))
-        prob = Problem(config, cells, parts=parts, rank=rank if distributed else 0)
+        prob = Problem(config, cells, parts=parts, rank=rank if distributed else 0,
+                       agglomerate_rows=args.agglomerate_rows if distributed else 0)
         solver, ns, x, b = prob.build_device(gsb, c)
         sync = barrier if distributed else (lambda: c.synchronize())
         mx = max_over_ranks if distributed else (lambda v: v)
@@ -460,7 +476,7 @@ def main():
     parity = None
     if world > 1 and not args.no_parity:
         pcells = 64
-        pp = Problem("c2", pcells, parts=PARTS[world], rank=rank)
+        pp = Problem("c2", pcells, parts=PARTS[world], rank=rank, agglomerate_rows=args.agglomerate_rows)
         psolver, pns, px, pb = pp.build_device(gsb, ctx)
         gsb.solve_(px, pns, pb)
         xerr = max_over_ranks(float(np.max(np.abs(px.get() - synth.exact_solution(pp.hh.levels[0])))))
@@ -549,6 +565,7 @@ def main():
         "config": {
             "workload": f"{prob.name}: {prob.what}, rtol 1e-8, x0=0",
             "partition": "x".join(str(p) for p in PARTS[world]), "levels_rows_rank0": prob.level_rows, "levels_nnz_rank0": prob.level_nnz,
+            "parts_per_level": ["x".join(str(q) for q in pl) for pl in (getattr(prob, "parts_per_level", None) or [])] or None,
             "fine_matrix_format": fmt,
             "l2_policy": "inputs larger than L2 (fine-level matrix %.0f MB as stored vs 126 MB L2); coarse levels are L2-resident by construction" % (fmt.get("bytes_per_pass", 0) / 1e6),
             "setup_s": round(prob.t_setup, 3), "host_generation_s": round(prob.t_gen, 3),

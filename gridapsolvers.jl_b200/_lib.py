@@ -38,6 +38,8 @@ SIGNATURES = {
     "gsb_profile_stop": [c_p, c_i, PP(c_i), c_p, c_p, c_p, c_p, c_p, c_p],
     "gsb_plan_create": [c_p, c_i64, c_i64, c_i, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_i, PP(c_p)],
     "gsb_plan_destroy": [c_p],
+    "gsb_redist_create": [c_p, c_i64, c_i64, c_i, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_i, PP(c_p)],
+    "gsb_vec_redistribute": [c_p, c_p, c_p],
     "gsb_mat_create": [c_p, c_i64, c_i64, c_i64, c_i, c_i, c_i, c_p, c_p, c_p, c_p, PP(c_p)],
     "gsb_mat_update_values": [c_p, c_p],
     "gsb_mat_info": [c_p, PP(c_i64), PP(c_i64), PP(c_i64), PP(c_i64)],
@@ -68,6 +70,7 @@ SIGNATURES = {
     "gsb_from_smoother_create": [c_p, c_p, PP(c_p)],
     "gsb_dense_lu_create": [c_p, PP(c_p)],
     "gsb_gmg_create": [c_p, c_i, PP(c_p), PP(c_p), PP(c_p), PP(c_p), PP(c_p), c_p, c_i, c_i, c_i, c_d, c_d, PP(c_p)],
+    "gsb_gmg_create_redist": [c_p, c_i, PP(c_p), PP(c_p), PP(c_p), PP(c_p), PP(c_p), c_p, c_i, c_i, c_i, c_d, c_d, PP(c_p), PP(c_p), PP(c_p)],
     "gsb_cg_create": [c_p, c_p, c_i, c_i, c_d, c_d, PP(c_p)],
     "gsb_gmres_create": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_d, c_d, PP(c_p)],
     "gsb_fgmres_create": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_d, c_d, PP(c_p)],

@@ -147,6 +147,35 @@ class ExchangePlan:
             pass
 
 
+class RedistributionPlan:
+    """Moves own values between two row partitions of the same global index space (MultilevelTools'
+    RedistributionOperator / redistribute_free_values!, GridTransferOperators.jl:447-532): one direction per plan."""
+
+    def __init__(self, ctx, n_src_own, n_dst_own, nbr_snd, snd_ptrs, snd_ids, nbr_rcv, rcv_ptrs, rcv_ids, index_base=0):
+        self.ctx = ctx
+        a32 = lambda v: np.ascontiguousarray(v, dtype=np.int32)
+        a64 = lambda v: np.ascontiguousarray(v, dtype=np.int64)
+        self._keep = (a32(nbr_snd), a64(snd_ptrs), a64(snd_ids), a32(nbr_rcv), a64(rcv_ptrs), a64(rcv_ids))
+        k = self._keep
+        h = c_p()
+        check(_lib.lib().gsb_redist_create(ctx.h, n_src_own, n_dst_own, len(k[0]), _ptr(k[0]), _ptr(k[1]), _ptr(k[2]),
+                                           len(k[3]), _ptr(k[3]), _ptr(k[4]), _ptr(k[5]), index_base, ctypes.byref(h)))
+        self.h, self.n_src_own, self.n_dst_own = h, n_src_own, n_dst_own
+
+    def __del__(self):
+        try:
+            if self.h:
+                _lib.lib().gsb_plan_destroy(self.h)
+        except Exception:
+            pass
+
+
+def redistribute_(dst, plan: "RedistributionPlan", src):
+    """dst (own values, destination layout) <- src (own values, source layout)"""
+    check(_lib.lib().gsb_vec_redistribute(plan.h, src.h, dst.h))
+    return dst
+
+
 class SparseMatrix:
     """Device mirror of the local block of a PSparseMatrix (own rows x own+ghost columns)."""
 
@@ -537,8 +566,13 @@ class GMGLinearSolver(LinearSolver):
     Transfer operators are explicit sparse matrices (P, and R = P^T for mode=:residual)."""
 
     def __init__(self, smatrices, interp, restrict, pre_smoothers=None, post_smoothers=None, coarsest_solver=None,
-                 mode="preconditioner", cycle_type="v_cycle", maxiter=100, atol=1.0e-14, rtol=1.0e-08, verbose=False):
+                 mode="preconditioner", cycle_type="v_cycle", maxiter=100, atol=1.0e-14, rtol=1.0e-08, verbose=False,
+                 redist=None):
+        """redist = (to_coarse, to_fine): per level boundary a RedistributionPlan pair (or None) for hierarchies whose
+        coarse levels live on fewer parts (the transfer operators then carry redist = Val{true} in the reference,
+        GridTransferOperators.jl:391-401,536-561)"""
         n = len(smatrices)
+        self.redist = redist
         if pre_smoothers is None:
             pre_smoothers = Fill(RichardsonSmoother(JacobiLinearSolver(), 10), n - 1)
         if post_smoothers is None:
@@ -562,9 +596,17 @@ class GMGLinearSolver(LinearSolver):
         coarse = _child(self.coarsest_solver, sm[n - 1])
         arr = lambda objs: (c_p * max(1, len(objs)))(*[o.h for o in objs])
         h = c_p()
-        check(_lib.lib().gsb_gmg_create(mat.ctx.h, n, arr(sm), arr(self.interp), arr(self.restrict), arr(pre), arr(post),
-                                        coarse.h, _MODES[self.mode], _CYCLES[self.cycle_type], self.log.tols.maxiter,
-                                        self.log.tols.atol, self.log.tols.rtol, ctypes.byref(h)))
+        if self.redist is None:
+            check(_lib.lib().gsb_gmg_create(mat.ctx.h, n, arr(sm), arr(self.interp), arr(self.restrict), arr(pre), arr(post),
+                                            coarse.h, _MODES[self.mode], _CYCLES[self.cycle_type], self.log.tols.maxiter,
+                                            self.log.tols.atol, self.log.tols.rtol, ctypes.byref(h)))
+        else:
+            parr = lambda plans: (c_p * max(1, len(plans)))(*[(p.h if p is not None else None) for p in plans])
+            tc, tf = self.redist
+            assert len(tc) == len(tf) == n - 1
+            check(_lib.lib().gsb_gmg_create_redist(mat.ctx.h, n, arr(sm), arr(self.interp), arr(self.restrict), arr(pre), arr(post),
+                                                   coarse.h, _MODES[self.mode], _CYCLES[self.cycle_type], self.log.tols.maxiter,
+                                                   self.log.tols.atol, self.log.tols.rtol, parr(tc), parr(tf), ctypes.byref(h)))
         kids = pre + ([] if post is pre else post) + [coarse]
         return NumericalSetup(self, h, kids, mat=mat)
 

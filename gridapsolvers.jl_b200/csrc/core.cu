@@ -289,31 +289,38 @@ static bool plan_active(gsb_vec_s &v, gsb_plan_t plan) {
   gsb_ctx_t ctx = v.ctx;
   if (!plan || ctx->nranks == 1) return false;
   if (plan->nbr_snd.empty() && plan->nbr_rcv.empty()) return false;
+  GSB_CHECK(!plan->redist, "consistent!/assemble!: this is a redistribution plan");
   GSB_CHECK(v.n_own == plan->n_own && v.n_ghost == plan->n_ghost, "consistent!: vector does not match the plan");
   return true;
 }
 
-static void exchange_on(gsb_vec_s &v, gsb_plan_t plan, cudaStream_t st) {
-  gsb_ctx_t ctx = v.ctx;
+// moves src[snd ids] of every rank into dst[rcv ids] of its neighbours (consistent!: src == dst, own -> ghost entries)
+static void exchange_on(gsb_ctx_t ctx, const double *src, double *dst, gsb_plan_t plan, cudaStream_t st) {
   const int64_t nsnd = plan->snd_ptrs.back(), nrcv = plan->rcv_ptrs.back();
   if (plan->p2p) {
     P2PPush ps{nsnd, plan->snd_ids.p, plan->snd_nbr.p, plan->snd_ptrs_dev.p, plan->peer_buf[0].p, plan->peer_buf[1].p,
                plan->peer_flag.p, (int)plan->nbr_snd.size(), plan->seq_dev.p, plan->ticket.p};
     const int g1 = (int)std::max<int64_t>(1, std::min<int64_t>((nsnd + 255) / 256, 2 * ctx->num_sms));
-    p2p_push_kernel<<<g1, 256, 0, st>>>(ps, v.d);
-    launched(ctx);
     const double *rb0 = (const double *)((char *)plan->block + plan->flag_bytes);
     const double *rb1 = rb0 + (size_t)std::max<int64_t>(nrcv, 1);
     P2PWait pw{(int)plan->nbr_rcv.size(), plan->nbr_rcv_dev.p, (const unsigned long long *)plan->block, plan->seq_dev.p, nrcv,
                plan->rcv_ids.p, rb0, rb1};
     const int g2 = (int)std::max<int64_t>(1, std::min<int64_t>((nrcv + 255) / 256, 2 * ctx->num_sms));
-    p2p_wait_unpack_kernel<<<g2, 256, 0, st>>>(pw, v.d);
+    if (ctx->opt("p2p_fused", "1") == "1" && plan->nbr_rcv.size() <= 256) {
+      // push, publish, wait and unpack in one launch (all blocks co-resident: <= 2 per SM)
+      p2p_exchange_kernel<<<std::max(g1, g2), 256, 0, st>>>(ps, pw, src, dst);
+      launched(ctx);
+      return;
+    }
+    p2p_push_kernel<<<g1, 256, 0, st>>>(ps, src);
+    launched(ctx);
+    p2p_wait_unpack_kernel<<<g2, 256, 0, st>>>(pw, dst);
     launched(ctx);
     return;
   }
   if (nsnd) {
     int grid = (int)std::min<int64_t>((nsnd + 255) / 256, 1024);
-    pack_kernel<<<grid, 256, 0, st>>>(nsnd, plan->snd_ids.p, v.d, plan->snd_buf.p);
+    pack_kernel<<<grid, 256, 0, st>>>(nsnd, plan->snd_ids.p, src, plan->snd_buf.p);
     launched(ctx);
   }
   GSB_NCCL(ncclGroupStart());
@@ -328,14 +335,14 @@ static void exchange_on(gsb_vec_s &v, gsb_plan_t plan, cudaStream_t st) {
   GSB_NCCL(ncclGroupEnd());
   if (nrcv) {
     int grid = (int)std::min<int64_t>((nrcv + 255) / 256, 1024);
-    unpack_kernel<<<grid, 256, 0, st>>>(nrcv, plan->rcv_ids.p, plan->rcv_buf.p, v.d);
+    unpack_kernel<<<grid, 256, 0, st>>>(nrcv, plan->rcv_ids.p, plan->rcv_buf.p, dst);
     launched(ctx);
   }
 }
 
 void consistent(gsb_vec_s &v, gsb_plan_t plan) {
   if (!plan_active(v, plan)) return;
-  exchange_on(v, plan, v.ctx->stream);
+  exchange_on(v.ctx, v.d, v.d, plan, v.ctx->stream);
 }
 
 // overlap: the exchange runs on the communication stream, ordered after everything already queued
@@ -345,7 +352,7 @@ void consistent_begin(gsb_vec_s &v, gsb_plan_t plan) {
   gsb_ctx_t ctx = v.ctx;
   GSB_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
   GSB_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_a, 0));
-  exchange_on(v, plan, ctx->comm_stream);
+  exchange_on(ctx, v.d, v.d, plan, ctx->comm_stream);
   GSB_CUDA(cudaEventRecord(ctx->ev_b, ctx->comm_stream));
 }
 // ... and the compute stream waits for the ghosts only before the ghost-column pass
@@ -395,6 +402,28 @@ void assemble(gsb_vec_s &v, gsb_plan_t plan) {
   }
   if (nsnd == 0 && nrcv == 0) return;
   if (v.n_ghost) GSB_CUDA(cudaMemsetAsync(v.d + v.n_own, 0, sizeof(double) * v.n_ghost, st));
+}
+
+// redistribute(plan, src, dst): dst[rcv ids] <- src[snd ids] of the ranks that hold them in the other partition
+// (MultilevelTools.redistribute_free_values! / RedistributionOperator, GridTransferOperators.jl:447-532: coarse
+// levels that live on fewer parts).  Same transport as consistent!; a rank may be its own neighbour.
+void redistribute(gsb_plan_t plan, gsb_vec_s &src, gsb_vec_s &dst) {
+  GSB_CHECK(plan && plan->redist, "redistribute: not a redistribution plan");
+  GSB_CHECK(src.n_own == plan->n_own && dst.n_own == plan->n_ghost, "redistribute: vectors do not match the plan");
+  GSB_CHECK(src.d != dst.d, "redistribute: source and destination alias");
+  gsb_ctx_t ctx = src.ctx;
+  if (ctx->nranks == 1) {  // one part on both sides: a permutation
+    const int64_t n = plan->snd_ptrs.back();
+    if (n) {
+      int grid = (int)std::min<int64_t>((n + 255) / 256, 1024);
+      pack_kernel<<<grid, 256, 0, ctx->stream>>>(n, plan->snd_ids.p, src.d, plan->snd_buf.p);
+      launched(ctx);
+      unpack_kernel<<<grid, 256, 0, ctx->stream>>>(n, plan->rcv_ids.p, plan->snd_buf.p, dst.d);
+      launched(ctx);
+    }
+    return;
+  }
+  exchange_on(ctx, src.d, dst.d, plan, ctx->stream);
 }
 
 // ---------------------------------------------------------------- row kernels
@@ -976,17 +1005,31 @@ static void setup_p2p(gsb_plan_s *p) {
     const int64_t nrcv_q = mq[0], off = mq[1 + me];
     GSB_CHECK(off >= 0, "p2p plan: neighbour " + std::to_string(q) + " does not expect data from rank " + std::to_string(me));
     void *base = nullptr;
-    if (cudaIpcOpenMemHandle(&base, hq, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-      ok = 0.0;
-      (void)cudaGetLastError();
-      break;
+    if (q == me) {
+      base = p->block;  // a rank can be its own neighbour in a redistribution plan; its block is not re-opened
+    } else {
+      if (cudaIpcOpenMemHandle(&base, hq, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        ok = 0.0;
+        (void)cudaGetLastError();
+        break;
+      }
+      p->peer_base[k] = base;
     }
-    p->peer_base[k] = base;
     const size_t fb = ((size_t)R * sizeof(unsigned long long) + 255) & ~(size_t)255;
     double *buf0 = (double *)((char *)base + fb);
     pb0[k] = buf0 + off;
     pb1[k] = buf0 + (size_t)std::max<int64_t>(nrcv_q, 1) + off;
     pf[k] = (unsigned long long *)base + me;
+  }
+  // the parity double buffer is safe only if a sender cannot run two exchanges ahead of a receiver: for a halo
+  // plan that needs a SYMMETRIC neighbour graph (I receive from exactly the ranks I send to; every rank checks its
+  // own lists, the verdict is collective).  Redistribution plans are one-directional by nature; their users
+  // alternate the forward and the reverse plan (GMG: restrict ... prolongate), which gives the same guarantee.
+  if (!p->redist) {
+    std::vector<int> a(p->nbr_snd), b(p->nbr_rcv);
+    std::sort(a.begin(), a.end());
+    std::sort(b.begin(), b.end());
+    if (a != b) ok = 0.0;
   }
   // collective verdict (also the barrier: nobody may push before every rank has zeroed its flags and
   // mapped its peers): sum of the per-rank ok flags must be R
@@ -1035,20 +1078,20 @@ static void setup_p2p(gsb_plan_s *p) {
   p->p2p = true;
 }
 
-int gsb_plan_create(gsb_ctx_t ctx, int64_t n_own, int64_t n_ghost, int n_nbr_snd, const int32_t *nbr_snd,
-                    const int64_t *snd_ptrs, const int64_t *snd_local_ids, int n_nbr_rcv, const int32_t *nbr_rcv,
-                    const int64_t *rcv_ptrs, const int64_t *rcv_local_ids, int index_base, gsb_plan_t *out) {
-  GSB_NULLCHK(ctx)
-  API_BEGIN
+static gsb_plan_t make_plan(gsb_ctx_t ctx, bool redist, int64_t n_own, int64_t n_ghost, int n_nbr_snd, const int32_t *nbr_snd,
+                            const int64_t *snd_ptrs, const int64_t *snd_local_ids, int n_nbr_rcv, const int32_t *nbr_rcv,
+                            const int64_t *rcv_ptrs, const int64_t *rcv_local_ids, int index_base) {
+  GSB_CHECK(n_own >= 0 && n_ghost >= 0 && n_nbr_snd >= 0 && n_nbr_rcv >= 0, "plan: negative size");
   std::unique_ptr<gsb_plan_s> p(new gsb_plan_s());
-  p->ctx = ctx; p->n_own = n_own; p->n_ghost = n_ghost;
+  p->ctx = ctx; p->n_own = n_own; p->n_ghost = n_ghost; p->redist = redist;
   p->nbr_snd.assign(nbr_snd, nbr_snd + n_nbr_snd);
   p->nbr_rcv.assign(nbr_rcv, nbr_rcv + n_nbr_rcv);
+  for (int q : p->nbr_snd) GSB_CHECK(q >= 0 && q < ctx->nranks && (redist || q != ctx->rank), "plan: bad send neighbour");
+  for (int q : p->nbr_rcv) GSB_CHECK(q >= 0 && q < ctx->nranks && (redist || q != ctx->rank), "plan: bad receive neighbour");
   p->snd_ptrs.resize((size_t)n_nbr_snd + 1);
   p->rcv_ptrs.resize((size_t)n_nbr_rcv + 1);
   for (int k = 0; k <= n_nbr_snd; ++k) p->snd_ptrs[(size_t)k] = snd_ptrs[k] - snd_ptrs[0];
   for (int k = 0; k <= n_nbr_rcv; ++k) p->rcv_ptrs[(size_t)k] = rcv_ptrs[k] - rcv_ptrs[0];
-  for (int k = 0; k < n_nbr_snd; ++k) { p->nbr_snd[(size_t)k] -= 0; }
   const int64_t nsnd = p->snd_ptrs.back(), nrcv = p->rcv_ptrs.back();
   std::vector<int> s((size_t)nsnd), r((size_t)nrcv);
   for (int64_t i = 0; i < nsnd; ++i) {
@@ -1056,9 +1099,10 @@ int gsb_plan_create(gsb_ctx_t ctx, int64_t n_own, int64_t n_ghost, int n_nbr_snd
     GSB_CHECK(id >= 0 && id < n_own, "plan: send id is not an own entry");
     s[(size_t)i] = (int)id;
   }
+  const int64_t r_lo = redist ? 0 : n_own, r_hi = redist ? n_ghost : n_own + n_ghost;
   for (int64_t i = 0; i < nrcv; ++i) {
     int64_t id = rcv_local_ids[i] - index_base;
-    GSB_CHECK(id >= n_own && id < n_own + n_ghost, "plan: receive id is not a ghost entry");
+    GSB_CHECK(id >= r_lo && id < r_hi, redist ? "redistribution plan: receive id is not an own entry of the destination" : "plan: receive id is not a ghost entry");
     r[(size_t)i] = (int)id;
   }
   p->snd_ids.alloc(std::max<size_t>(1, s.size()));
@@ -1071,7 +1115,26 @@ int gsb_plan_create(gsb_ctx_t ctx, int64_t n_own, int64_t n_ghost, int n_nbr_snd
   GSB_CUDA(cudaDeviceSynchronize());
   if (ctx->nranks > 1 && ctx->opt("p2p", "1") == "1") setup_p2p(p.get());
   if (ctx->nranks > 1 && !p->p2p) ctx->nccl_halo_in_use = true;
-  *out = p.release();
+  return p.release();
+}
+
+int gsb_plan_create(gsb_ctx_t ctx, int64_t n_own, int64_t n_ghost, int n_nbr_snd, const int32_t *nbr_snd,
+                    const int64_t *snd_ptrs, const int64_t *snd_local_ids, int n_nbr_rcv, const int32_t *nbr_rcv,
+                    const int64_t *rcv_ptrs, const int64_t *rcv_local_ids, int index_base, gsb_plan_t *out) {
+  GSB_NULLCHK(ctx)
+  API_BEGIN
+  *out = make_plan(ctx, false, n_own, n_ghost, n_nbr_snd, nbr_snd, snd_ptrs, snd_local_ids, n_nbr_rcv, nbr_rcv, rcv_ptrs,
+                   rcv_local_ids, index_base);
+  API_END(ctx)
+}
+
+int gsb_redist_create(gsb_ctx_t ctx, int64_t n_src_own, int64_t n_dst_own, int n_nbr_snd, const int32_t *nbr_snd,
+                      const int64_t *snd_ptrs, const int64_t *snd_local_ids, int n_nbr_rcv, const int32_t *nbr_rcv,
+                      const int64_t *rcv_ptrs, const int64_t *rcv_local_ids, int index_base, gsb_plan_t *out) {
+  GSB_NULLCHK(ctx)
+  API_BEGIN
+  *out = make_plan(ctx, true, n_src_own, n_dst_own, n_nbr_snd, nbr_snd, snd_ptrs, snd_local_ids, n_nbr_rcv, nbr_rcv, rcv_ptrs,
+                   rcv_local_ids, index_base);
   API_END(ctx)
 }
 
@@ -1148,6 +1211,16 @@ int gsb_vec_consistent(gsb_vec_t v, gsb_plan_t plan) {
   gsb::consistent(*v, plan);
   GSB_CUDA(cudaStreamSynchronize(v->ctx->stream));
   API_END(v->ctx)
+}
+
+int gsb_vec_redistribute(gsb_plan_t plan, gsb_vec_t src, gsb_vec_t dst) {
+  GSB_NULLCHK(plan)
+  GSB_NULLCHK(src)
+  GSB_NULLCHK(dst)
+  API_BEGIN
+  gsb::redistribute(plan, *src, *dst);
+  GSB_CUDA(cudaStreamSynchronize(src->ctx->stream));
+  API_END(src->ctx)
 }
 
 int gsb_vec_assemble(gsb_vec_t v, gsb_plan_t plan) {

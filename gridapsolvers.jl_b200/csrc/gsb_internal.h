@@ -112,6 +112,8 @@ struct gsb_plan_s {
   std::vector<int64_t> snd_ptrs, rcv_ptrs;  // per-neighbour offsets into the id lists
   gsb::DevBuf<int> snd_ids, rcv_ids;        // 0-based local ids
   gsb::DevBuf<double> snd_buf, rcv_buf;
+  bool redist = false;          // redistribution plan: n_own = own size of the source layout, n_ghost = own size of the
+                                // destination layout, rcv ids index OWN entries of the destination vector
   bool rcv_contiguous = false;  // ghosts of each neighbour form one ascending run -> no unpack
   // NVLink peer-memory exchange (CUDA IPC); see kernels.cuh p2p_push_kernel
   bool p2p = false;

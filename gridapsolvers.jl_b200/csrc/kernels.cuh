@@ -672,6 +672,48 @@ __global__ void __launch_bounds__(256) p2p_wait_unpack_kernel(P2PWait w, double 
     v[w.rcv_ids[i]] = __ldcg(rcv_buf + i);
 }
 
+// the whole exchange in ONE launch: every block pushes its share, the last block to finish publishes the sequence
+// number to the neighbours, then all blocks wait for the neighbours' numbers and unpack.  The grid is never larger
+// than what is co-resident (<= 2 blocks per SM), so the blocks that spin cannot starve the block that publishes.
+__global__ void __launch_bounds__(256) p2p_exchange_kernel(P2PPush p, P2PWait w, const double *v, double *vdst) {
+  const unsigned long long seq = *(volatile unsigned long long *)p.seq + 1ull;  // this exchange's number
+  double *const *peer_buf = (seq & 1ull) ? p.peer_buf1 : p.peer_buf0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.nsnd; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = p.snd_nbr[i];
+    peer_buf[k][i - p.snd_ptrs[k]] = v[p.snd_ids[i]];
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool is_last;
+  if (threadIdx.x == 0) is_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (is_last) {
+    __threadfence_system();
+    for (int k = threadIdx.x; k < p.n_nbr; k += blockDim.x) {
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.peer_flag[k]), "l"(seq) : "memory");
+    }
+    if (threadIdx.x == 0) {
+      *p.ticket = 0u;
+      *p.seq = seq;  // every block has read the old value before arriving at the ticket
+    }
+  }
+  const double *rcv_buf = (seq & 1ull) ? w.rcv_buf1 : w.rcv_buf0;
+  if (threadIdx.x < w.n_nbr) {
+    const unsigned long long *f = w.flags + w.nbr_rank[threadIdx.x];
+    const long long t0 = clock64();
+    for (;;) {
+      unsigned long long cur;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(cur) : "l"(f) : "memory");
+      if (cur >= seq) break;
+      if (clock64() - t0 > 20000000000LL) __trap();  // ~10 s: a peer died; fail instead of hanging
+      __nanosleep(32);
+    }
+  }
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < w.nrcv; i += (int64_t)gridDim.x * blockDim.x)
+    vdst[w.rcv_ids[i]] = __ldcg(rcv_buf + i);
+}
+
 // invd[i] = 1/A[i,i]  (JacobiLinearSolvers.jl:20-23,29-34; diagonal of the own-own block, kept per matrix)
 __global__ void inv_diag_kernel(int64_t nrows, const double *__restrict__ diag, double *__restrict__ invd) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -51,6 +51,8 @@ void mgs_step(gsb_vec_s &w, const gsb_vec_s *vprev, int slot_prev, const gsb_vec
 void multi_axpy(gsb_vec_s &x, const std::vector<const gsb_vec_s *> &z, const double *g);
 // assemble!(v): ghost -> owner accumulation through the reversed plan, then ghosts zeroed
 void assemble(gsb_vec_s &v, gsb_plan_t plan);
+// redistribution of own values between two row partitions (plan created by gsb_redist_create)
+void redistribute(gsb_plan_t plan, gsb_vec_s &src, gsb_vec_s &dst);
 
 // dense coarse solver pieces
 void dense_inverse_rows(gsb_mat_t A, DevBuf<double> &inv_rows, int64_t &n_global, int64_t &row_off);

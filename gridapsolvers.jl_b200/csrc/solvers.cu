@@ -164,7 +164,8 @@ struct GMGNS : gsb_solver_s {
   std::vector<gsb_solver_t> pre, post;
   gsb_solver_t coarse;
   VecP rh;  // finest level cache, GMGLinearSolvers.jl:391-396
-  struct Work { VecP dxh, Adxh, dxH, rH, tP, tR; };
+  struct Work { VecP dxh, Adxh, dxH, rH, tP, tR, dxH_red, rH_red; };
+  std::vector<gsb_plan_t> to_coarse, to_fine;  // per level boundary: redistribution plans (nullptr: same parts)
   std::vector<Work> work;  // :451-466
   Slots slots;
   int slot_rr;
@@ -172,7 +173,8 @@ struct GMGNS : gsb_solver_s {
   const char *name() const override { return "GMG"; }
   gsb_mat_t matrix() override { return mats[0]; }
   GMGNS(gsb_ctx_t c, int nlev_, const gsb_mat_t *m, const gsb_mat_t *ip, const gsb_mat_t *rs, const gsb_solver_t *pr,
-        const gsb_solver_t *po, gsb_solver_t cs, int mode_, int cyc, int maxiter, double atol, double rtol)
+        const gsb_solver_t *po, gsb_solver_t cs, int mode_, int cyc, int maxiter, double atol, double rtol,
+        const gsb_plan_t *to_coarse_ = nullptr, const gsb_plan_t *to_fine_ = nullptr)
       : nlev(nlev_), mode(mode_), cycle_type(cyc), coarse(cs) {
     ctx = c;
     GSB_CHECK(nlev >= 1, "GMG: need at least one level");
@@ -183,6 +185,13 @@ struct GMGNS : gsb_solver_s {
     restrict_.assign(rs, rs + nlev - 1);
     pre.assign(pr, pr + nlev - 1);
     post.assign(po, po + nlev - 1);
+    to_coarse.assign((size_t)std::max(nlev - 1, 0), nullptr);
+    to_fine.assign((size_t)std::max(nlev - 1, 0), nullptr);
+    for (int l = 0; l < nlev - 1; ++l) {
+      if (to_coarse_) to_coarse[(size_t)l] = to_coarse_[l];
+      if (to_fine_) to_fine[(size_t)l] = to_fine_[l];
+      GSB_CHECK((to_coarse[(size_t)l] == nullptr) == (to_fine[(size_t)l] == nullptr), "GMG: a redistributed level needs both plans");
+    }
     log.configure(maxiter, atol, rtol);
     has_log = true;
     slots.take(ctx, 2);
@@ -196,17 +205,34 @@ struct GMGNS : gsb_solver_s {
     work.resize((size_t)nlev - 1);
     for (int l = 0; l < nlev - 1; ++l) {
       Work &w = work[(size_t)l];
-      GSB_CHECK(interp[(size_t)l]->n_rows == mats[(size_t)l]->n_rows && interp[(size_t)l]->n_own_cols == mats[(size_t)l + 1]->n_rows,
-                "GMG: prolongation shape mismatch at level " + std::to_string(l + 1));
-      GSB_CHECK(restrict_[(size_t)l]->n_rows == mats[(size_t)l + 1]->n_rows && restrict_[(size_t)l]->n_own_cols == mats[(size_t)l]->n_rows,
-                "GMG: restriction shape mismatch at level " + std::to_string(l + 1));
+      const bool red = to_coarse[(size_t)l] != nullptr;
+      GSB_CHECK(interp[(size_t)l]->n_rows == mats[(size_t)l]->n_rows && restrict_[(size_t)l]->n_own_cols == mats[(size_t)l]->n_rows,
+                "GMG: transfer operator shape mismatch (fine side) at level " + std::to_string(l + 1));
+      if (!red) {
+        GSB_CHECK(interp[(size_t)l]->n_own_cols == mats[(size_t)l + 1]->n_rows,
+                  "GMG: prolongation shape mismatch at level " + std::to_string(l + 1));
+        GSB_CHECK(restrict_[(size_t)l]->n_rows == mats[(size_t)l + 1]->n_rows,
+                  "GMG: restriction shape mismatch at level " + std::to_string(l + 1));
+      } else {
+        // level l+2 lives on another (smaller) set of parts: P / R act on the coarse space in the partition of
+        // level l+1's parts, the plans move own values between the two layouts (GridTransferOperators.jl:391-401,
+        // 536-561 with Val{true}: redistribute_free_values! before the interpolation / after the restriction)
+        gsb_plan_t tc = to_coarse[(size_t)l], tf = to_fine[(size_t)l];
+        GSB_CHECK(tc->redist && tf->redist, "GMG: redistribution plans expected");
+        GSB_CHECK(tc->n_own == restrict_[(size_t)l]->n_rows && tc->n_ghost == mats[(size_t)l + 1]->n_rows,
+                  "GMG: to-coarse redistribution plan does not match level " + std::to_string(l + 2));
+        GSB_CHECK(tf->n_own == mats[(size_t)l + 1]->n_rows && tf->n_ghost == interp[(size_t)l]->n_own_cols,
+                  "GMG: to-fine redistribution plan does not match level " + std::to_string(l + 2));
+        w.rH_red = range_vec(restrict_[(size_t)l]);
+        w.dxH_red = domain_vec(interp[(size_t)l]);
+      }
       w.dxh = domain_vec(mats[(size_t)l]);
       w.Adxh = range_vec(mats[(size_t)l]);
       w.dxH = domain_vec(mats[(size_t)l + 1]);
       w.rH = domain_vec(mats[(size_t)l + 1]);
       // transfer operators may use a different ghost layout than the level matrices ("FE layout"
       // vs "matrix layout", GridTransferOperators.jl:395-398): stage through a copy of own values
-      if (interp[(size_t)l]->plan != mats[(size_t)l + 1]->plan || interp[(size_t)l]->n_ghost_cols != mats[(size_t)l + 1]->n_ghost_cols)
+      if (!red && (interp[(size_t)l]->plan != mats[(size_t)l + 1]->plan || interp[(size_t)l]->n_ghost_cols != mats[(size_t)l + 1]->n_ghost_cols))
         w.tP = domain_vec(interp[(size_t)l]);
       if (restrict_[(size_t)l]->plan != mats[(size_t)l]->plan || restrict_[(size_t)l]->n_ghost_cols != mats[(size_t)l]->n_ghost_cols)
         w.tR = domain_vec(restrict_[(size_t)l]);
@@ -219,6 +245,7 @@ struct GMGNS : gsb_solver_s {
     Work &w = work[(size_t)lev];
     gsb_mat_t P = interp[(size_t)lev], Ah = mats[(size_t)lev];
     Vec *src = w.dxH.get();
+    if (to_fine[(size_t)lev]) { redistribute(to_fine[(size_t)lev], *w.dxH, *w.dxH_red); src = w.dxH_red.get(); }
     if (w.tP) { vec_copy(*w.tP, *w.dxH); src = w.tP.get(); }
     spmv_add(P, *src, *w.dxh, xh);     // :491,494  dxh = P dxH ; xh .= xh .+ dxh
     resid(Ah, *w.dxh, rh_, rh_);       // :495-496  rh .= rh .- Ah dxh
@@ -227,7 +254,12 @@ struct GMGNS : gsb_solver_s {
     Work &w = work[(size_t)lev];
     Vec *src = &rh_;
     if (w.tR) { vec_copy(*w.tR, rh_); src = w.tR.get(); }
-    spmv(restrict_[(size_t)lev], *src, *w.rH, 1.0, 0.0);  // :484
+    if (to_coarse[(size_t)lev]) {
+      spmv(restrict_[(size_t)lev], *src, *w.rH_red, 1.0, 0.0);  // :484 then redistribute_free_values!
+      redistribute(to_coarse[(size_t)lev], *w.rH_red, *w.rH);
+    } else {
+      spmv(restrict_[(size_t)lev], *src, *w.rH, 1.0, 0.0);  // :484
+    }
     vec_fill(*w.dxH, 0.0);                                // :487
   }
   void cycle(int kind, int lev, Vec &xh, Vec &rh_) {  // gmg_v_cycle! :468-502, w :504-556, f :558-610
@@ -235,15 +267,61 @@ struct GMGNS : gsb_solver_s {
     Work &w = work[(size_t)lev];
     pre[(size_t)lev]->solve(xh, rh_);             // :481
     restrict_residual(lev, rh_);
-    cycle(kind, lev + 1, *w.dxH, *w.rH);          // :488 / :524 / :578
+    coarser(kind, lev);                           // :488 / :524 / :578
     correct(lev, xh, rh_);
     if (kind != GSB_V_CYCLE) {
       post[(size_t)lev]->solve(xh, rh_);          // re-smooth :533 / :587
       restrict_residual(lev, rh_);
-      cycle(kind == GSB_W_CYCLE ? GSB_W_CYCLE : GSB_V_CYCLE, lev + 1, *w.dxH, *w.rH);  // :540 / :594
+      coarser(kind == GSB_W_CYCLE ? GSB_W_CYCLE : GSB_V_CYCLE, lev);  // :540 / :594
       correct(lev, xh, rh_);
     }
     post[(size_t)lev]->solve(xh, rh_);            // :499
+  }
+  // the recursive call of a cycle on level lev+1.  Below the finest level a cycle always works on the SAME vectors
+  // (the level's dxH / rH work vectors), whatever pair (x, b) the caller of the solver passed: the sub-cycle from
+  // the second level down -- a few hundred tiny launches -- is captured once per cycle kind into a CUDA graph and
+  // replayed, in every mode (mode=:solver iterations, FGMRES's changing vector pairs, ...).
+  cudaGraphExec_t sub_exec[3] = {nullptr, nullptr, nullptr};
+  int64_t sub_launches[3] = {0, 0, 0};
+  bool sub_failed = false, in_capture = false;
+  bool graphs_allowed() const {
+    return !ctx->profiling && ctx->opt("graph", "1") == "1" && children_capturable &&
+           (ctx->nranks == 1 || (!ctx->nccl_halo_in_use && ctx->opt("overlap", "0") != "1"));
+  }
+  void coarser(int kind, int lev) {
+    Work &w = work[(size_t)lev];
+    const int gi = kind == GSB_V_CYCLE ? 0 : (kind == GSB_W_CYCLE ? 1 : 2);
+    if (lev != 0 || nlev <= 2 || in_capture || sub_failed || !graphs_allowed() || ctx->opt("gmg_subgraph", "1") != "1") {
+      cycle(kind, lev + 1, *w.dxH, *w.rH);
+      return;
+    }
+    if (!sub_exec[gi]) {
+      const int64_t l0 = ctx->launches;
+      cudaGraph_t g = nullptr;
+      bool ok = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      if (ok) {
+        in_capture = true;
+        try {
+          cycle(kind, 1, *w.dxH, *w.rH);
+        } catch (...) {
+          ok = false;
+        }
+        in_capture = false;
+        if (cudaStreamEndCapture(ctx->stream, &g) != cudaSuccess || g == nullptr) ok = false;
+        if (ok && cudaGraphInstantiate(&sub_exec[gi], g, 0) != cudaSuccess) { ok = false; sub_exec[gi] = nullptr; }
+        if (g) cudaGraphDestroy(g);
+      }
+      sub_launches[gi] = ctx->launches - l0;
+      ctx->launches = l0;
+      if (!ok) {
+        (void)cudaGetLastError();
+        sub_failed = true;
+        cycle(kind, 1, *w.dxH, *w.rH);
+        return;
+      }
+    }
+    GSB_CUDA(cudaGraphLaunch(sub_exec[gi], ctx->stream));
+    ctx->launches += sub_launches[gi];
   }
   double norm_rh() {
     dot(*rh, *rh, slot_rr);
@@ -269,8 +347,7 @@ struct GMGNS : gsb_solver_s {
       // coarse-level kernels) is captured once into a CUDA graph and replayed
       // (multi-rank: NCCL collectives are capturable and the peer-memory halo exchange keeps its
       //  sequence number on the device, so the replay is valid there too; the two-stream overlap is not)
-      const bool use_graph = !ctx->profiling && ctx->opt("graph", "1") == "1" && children_capturable && !graph_failed &&
-                             (ctx->nranks == 1 || (!ctx->nccl_halo_in_use && ctx->opt("overlap", "0") != "1"));
+      const bool use_graph = graphs_allowed() && !graph_failed;
       if (use_graph && graph_exec && graph_x == x.d && graph_b == b.d) {
         GSB_CUDA(cudaGraphLaunch(graph_exec, ctx->stream));
         ctx->launches += graph_launches;
@@ -282,6 +359,7 @@ struct GMGNS : gsb_solver_s {
         cudaGraph_t g = nullptr;
         bool ok = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
         if (ok) {
+          in_capture = true;  // the sub-cycle graph is not nested into this capture: everything is recorded flat
           try {
             dot(*rh, *rh, slot_rr);
             cycle(cycle_type, 0, x, *rh);
@@ -289,6 +367,7 @@ struct GMGNS : gsb_solver_s {
           } catch (...) {
             ok = false;
           }
+          in_capture = false;
           if (cudaStreamEndCapture(ctx->stream, &g) != cudaSuccess || g == nullptr) ok = false;
           if (ok && cudaGraphInstantiate(&graph_exec, g, 0) != cudaSuccess) { ok = false; graph_exec = nullptr; }
           if (g) cudaGraphDestroy(g);
@@ -330,6 +409,8 @@ struct GMGNS : gsb_solver_s {
   int64_t graph_launches = 0;
   ~GMGNS() override {
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    for (cudaGraphExec_t e : sub_exec)
+      if (e) cudaGraphExecDestroy(e);
   }
   void finish() override {
     if (!pending) return;
@@ -831,6 +912,15 @@ int gsb_gmg_create(gsb_ctx_t ctx, int nlev, const gsb_mat_t *mats, const gsb_mat
   GSB_NULLCHK(ctx)
   API_BEGIN
   *out = new GMGNS(ctx, nlev, mats, interp, restrict_, pre, post, coarsest, mode, cycle_type, maxiter, atol, rtol);
+  API_END(ctx)
+}
+int gsb_gmg_create_redist(gsb_ctx_t ctx, int nlev, const gsb_mat_t *mats, const gsb_mat_t *interp, const gsb_mat_t *restrict_,
+                          const gsb_solver_t *pre, const gsb_solver_t *post, gsb_solver_t coarsest, int mode, int cycle_type,
+                          int maxiter, double atol, double rtol, const gsb_plan_t *to_coarse, const gsb_plan_t *to_fine,
+                          gsb_solver_t *out) {
+  GSB_NULLCHK(ctx)
+  API_BEGIN
+  *out = new GMGNS(ctx, nlev, mats, interp, restrict_, pre, post, coarsest, mode, cycle_type, maxiter, atol, rtol, to_coarse, to_fine);
   API_END(ctx)
 }
 int gsb_cg_create(gsb_mat_t A, gsb_solver_t Pl, int flexible, int maxiter, double atol, double rtol, gsb_solver_t *out) {

@@ -241,6 +241,65 @@ def to_scipy(rowptr, col, val, ncols):
     return sp.csr_matrix((val, col, rowptr), shape=(rowptr.shape[0] - 1, ncols))
 
 
+def empty_level_part(ncell, parts, rank, lengths=None) -> LevelPart:
+    """the part of a rank that does not hold this level (levels on fewer parts, HierarchicalArrays.jl:96-149)"""
+    d = len(ncell)
+    z = lambda: np.zeros(d, dtype=np.int64)
+    i32, i64 = (lambda n: np.zeros(n, dtype=np.int32)), (lambda n: np.zeros(n, dtype=np.int64))
+    return LevelPart(tuple(int(n) for n in ncell), tuple(int(q) for q in parts), rank, z(), z(), z(), z(), i32(0), 0, 0, i32(0), i64(0),
+                     tuple(float(v) for v in (lengths if lengths is not None else (1.0,) * d)), i32(0), i64(1), i64(0), i32(0), i64(1), i64(0))
+
+
+def level_part_or_empty(ncell, parts, rank, lengths=None) -> LevelPart:
+    return make_level_part(ncell, parts, rank, lengths) if rank < int(np.prod(parts)) else empty_level_part(ncell, parts, rank, lengths)
+
+
+def _owner_of(ncell, parts, X):
+    """(owner rank, owner-local id) of the free nodes X (N,d) in the Cartesian partition `parts` of the mesh `ncell`"""
+    d = len(ncell)
+    per = np.array([ncell[k] // parts[k] for k in range(d)], dtype=np.int64)
+    q = np.minimum(X // per, np.array(parts, dtype=np.int64) - 1)
+    owner = np.zeros(X.shape[0], dtype=np.int64)
+    stride = 1
+    for k in range(d):
+        owner += q[:, k] * stride
+        stride *= parts[k]
+    lid = np.zeros(X.shape[0], dtype=np.int64)
+    for r in np.unique(owner):
+        m = owner == r
+        c = part_coords(int(r), parts)
+        rlo = np.array([own_range(ncell[k], parts[k], c[k])[0] for k in range(d)])
+        rhi = np.array([own_range(ncell[k], parts[k], c[k])[1] for k in range(d)])
+        lid[m] = _box_lids(rlo, rhi, X[m])
+    return owner, lid
+
+
+def redistribution_lists(ncell, src_parts, dst_parts, rank):
+    """Neighbour / id lists that move the own free-dof values of the mesh `ncell` from the partition `src_parts` to the
+    partition `dst_parts` (part grids over the same ranks, a grid with fewer parts leaves the last ranks empty): the
+    data of MultilevelTools' RedistributionOperator (GridTransferOperators.jl:447-532) for Cartesian partitions.
+    Sender and receiver derive the same order independently: per neighbour, ascending SOURCE local id.
+    Returns (n_src_own, n_dst_own, nbr_snd, snd_ptrs, snd_ids, nbr_rcv, rcv_ptrs, rcv_ids)."""
+    ncell = tuple(int(n) for n in ncell)
+    src, dst = level_part_or_empty(ncell, src_parts, rank), level_part_or_empty(ncell, dst_parts, rank)
+
+    def grouped(owner, key):
+        order = np.lexsort((key, owner))
+        nbr, counts = np.unique(owner, return_counts=True)
+        return nbr.astype(np.int32), np.concatenate([[0], np.cumsum(counts)]).astype(np.int64), order.astype(np.int64)
+
+    e32, e64 = np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int64)
+    nbr_snd, snd_ptrs, snd_ids = e32, np.zeros(1, dtype=np.int64), e64
+    nbr_rcv, rcv_ptrs, rcv_ids = e32, np.zeros(1, dtype=np.int64), e64
+    if src.n_own:
+        owner, _ = _owner_of(ncell, dst_parts, _box_coords(src.olo, src.ohi))
+        nbr_snd, snd_ptrs, snd_ids = grouped(owner, np.arange(src.n_own))
+    if dst.n_own:
+        sowner, slid = _owner_of(ncell, src_parts, _box_coords(dst.olo, dst.ohi))
+        nbr_rcv, rcv_ptrs, rcv_ids = grouped(sowner, slid)
+    return src.n_own, dst.n_own, nbr_snd, snd_ptrs, snd_ids, nbr_rcv, rcv_ptrs, rcv_ids
+
+
 @dataclass
 class HostHierarchy:
     """Host (numpy) arrays of one rank's part of the level hierarchy."""
@@ -250,27 +309,57 @@ class HostHierarchy:
     P: list
     R: list
     b: np.ndarray
+    # levels on fewer parts: per level boundary l (None = same parts on both sides) the coarse space of level l+1 in
+    # the partition of level l's parts (columns of P[l] / rows of R[l]) and the two redistribution list sets
+    coarse_red: list = None
+    to_coarse: list = None
+    to_fine: list = None
 
 
-def poisson_hierarchy_host(ncell_fine, nlevels, parts=None, rank=0, lengths=None) -> HostHierarchy:
+def _empty_rows():
+    return np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.float64)
+
+
+def poisson_hierarchy_host(ncell_fine, nlevels, parts=None, rank=0, lengths=None, parts_per_level=None) -> HostHierarchy:
+    """parts_per_level[l]: part grid of level l (default: `parts` on every level).  A level whose grid has fewer parts
+    than ranks lives on the first ranks only (ModelHierarchy's np_per_level); the transfer operators across such a
+    boundary act on the coarse space partitioned like the FINER level and come with redistribution lists."""
     d = len(ncell_fine)
     parts = tuple(parts) if parts is not None else (1,) * d
+    ppl = [tuple(q) for q in parts_per_level] if parts_per_level is not None else [parts] * nlevels
+    assert len(ppl) == nlevels and ppl[0] == parts
     levels, As = [], []
     nc = tuple(int(n) for n in ncell_fine)
+    ncs = []
     b0 = None
     for l in range(nlevels):
-        lp = make_level_part(nc, parts, rank, lengths)
-        rowptr, col, val, b = poisson_rows(lp)
+        lp = level_part_or_empty(nc, ppl[l], rank, lengths)
+        if lp.n_own:
+            rowptr, col, val, b = poisson_rows(lp)
+        else:
+            (rowptr, col, val), b = _empty_rows(), np.zeros(0)
         if l == 0:
             b0 = b
         levels.append(lp)
+        ncs.append(nc)
         As.append((rowptr, col, val))
         if l < nlevels - 1:
             assert all(n % 2 == 0 for n in nc)
             nc = tuple(n // 2 for n in nc)
-    Ps = [prolong_rows(levels[l], levels[l + 1]) for l in range(nlevels - 1)]
-    Rs = [restrict_rows(levels[l], levels[l + 1]) for l in range(nlevels - 1)]
-    return HostHierarchy(levels, As, Ps, Rs, b0)
+    Ps, Rs, cred, tc, tf = [], [], [], [], []
+    for l in range(nlevels - 1):
+        fine = levels[l]
+        if ppl[l + 1] == ppl[l]:
+            coarse = levels[l + 1]
+            cred.append(None); tc.append(None); tf.append(None)
+        else:
+            coarse = level_part_or_empty(ncs[l + 1], ppl[l], rank, lengths)  # coarse space on the finer level's parts
+            cred.append(coarse)
+            tc.append(redistribution_lists(ncs[l + 1], ppl[l], ppl[l + 1], rank))
+            tf.append(redistribution_lists(ncs[l + 1], ppl[l + 1], ppl[l], rank))
+        Ps.append(prolong_rows(fine, coarse) if fine.n_own else _empty_rows())
+        Rs.append(restrict_rows(fine, coarse) if coarse.n_own else _empty_rows())
+    return HostHierarchy(levels, As, Ps, Rs, b0, cred, tc, tf)
 
 
 @dataclass
@@ -281,24 +370,46 @@ class DeviceHierarchy:
     A: list
     P: list
     R: list
+    to_coarse: list = None  # RedistributionPlan per level boundary (None: same parts)
+    to_fine: list = None
+    plans_red: list = None
+
+    @property
+    def redist(self):
+        """the `redist=` argument of GMGLinearSolver (None when no level is redistributed)"""
+        if not self.to_coarse or all(t is None for t in self.to_coarse):
+            return None
+        return self.to_coarse, self.to_fine
 
 
 def upload_hierarchy(ctx, hh: HostHierarchy) -> DeviceHierarchy:
-    """numerical_setup-side upload: PSparseMatrix mirrors + exchange plans per level."""
-    from .api import ExchangePlan, SparseMatrix
+    """numerical_setup-side upload: PSparseMatrix mirrors + exchange plans per level (+ redistribution plans where a
+    level lives on fewer parts).  Every rank creates every plan, in the same order (plan creation is collective)."""
+    from .api import ExchangePlan, RedistributionPlan, SparseMatrix
+
+    def mkplan(lp):
+        if ctx.nranks == 1:
+            return None
+        return ExchangePlan(ctx, lp.n_own, lp.n_ghost, lp.nbr_snd, lp.snd_ptrs, lp.snd_ids, lp.nbr_rcv, lp.rcv_ptrs, lp.rcv_ids)
 
     plans, As, Ps, Rs = [], [], [], []
     for lp, (rp, c, v) in zip(hh.levels, hh.A):
-        plan = None
-        if ctx.nranks > 1:
-            plan = ExchangePlan(ctx, lp.n_own, lp.n_ghost, lp.nbr_snd, lp.snd_ptrs, lp.snd_ids, lp.nbr_rcv, lp.rcv_ptrs, lp.rcv_ids)
+        plan = mkplan(lp)
         plans.append(plan)
         As.append(SparseMatrix(ctx, lp.n_own, lp.n_own, lp.n_ghost, rp, c, v, plan=plan))
+    nb = len(hh.P)
+    cred = hh.coarse_red or [None] * nb
+    to_coarse, to_fine, plans_red = [None] * nb, [None] * nb, [None] * nb
     for l, ((rp, c, v), (rr, rc, rv)) in enumerate(zip(hh.P, hh.R)):
-        f, co = hh.levels[l], hh.levels[l + 1]
-        Ps.append(SparseMatrix(ctx, f.n_own, co.n_own, co.n_ghost, rp, c, v, plan=plans[l + 1]))
+        f, co, pco = hh.levels[l], hh.levels[l + 1], plans[l + 1]
+        if cred[l] is not None:
+            co = cred[l]
+            pco = plans_red[l] = mkplan(co)
+            to_coarse[l] = RedistributionPlan(ctx, *hh.to_coarse[l])
+            to_fine[l] = RedistributionPlan(ctx, *hh.to_fine[l])
+        Ps.append(SparseMatrix(ctx, f.n_own, co.n_own, co.n_ghost, rp, c, v, plan=pco))
         Rs.append(SparseMatrix(ctx, co.n_own, f.n_own, f.n_ghost, rr, rc, rv, plan=plans[l]))
-    return DeviceHierarchy(ctx, hh, plans, As, Ps, Rs)
+    return DeviceHierarchy(ctx, hh, plans, As, Ps, Rs, to_coarse, to_fine, plans_red)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -102,6 +102,21 @@ int gsb_plan_create(gsb_ctx_t ctx, int64_t n_own, int64_t n_ghost, int n_nbr_snd
                     const int32_t *nbr_rcv, const int64_t *rcv_ptrs, const int64_t *rcv_local_ids,
                     int index_base, gsb_plan_t *out);
 int gsb_plan_destroy(gsb_plan_t plan);
+/* Redistribution plan: moves the OWN values of a vector between two row partitions of the same global index space
+ * (the same plan type and transport as the exchange plan; destroy with gsb_plan_destroy).  snd_local_ids index own
+ * entries of the SOURCE layout (n_src_own of them on this rank) to send to each neighbour, rcv_local_ids own entries
+ * of the DESTINATION layout (n_dst_own) to fill; a rank may list itself as a neighbour.  Replaces: MultilevelTools
+ * RedistributionOperator / redistribute_free_values! (MultilevelTools/GridTransferOperators.jl:2-157,447-532,
+ * RedistributionOperators.jl) and the level-on-fewer-parts semantics of HierarchicalArrays.jl:96-149 (a rank that
+ * does not hold a level passes matrices / vectors with zero own rows).  COLLECTIVE like gsb_plan_create.  The two
+ * directions of a repartition are two plans; callers alternate them (restrict ... prolongate), which is what keeps
+ * the double-buffered peer-memory transport safe for the one-directional neighbour graph of a redistribution. */
+int gsb_redist_create(gsb_ctx_t ctx, int64_t n_src_own, int64_t n_dst_own, int n_nbr_snd, const int32_t *nbr_snd,
+                      const int64_t *snd_ptrs, const int64_t *snd_local_ids, int n_nbr_rcv,
+                      const int32_t *nbr_rcv, const int64_t *rcv_ptrs, const int64_t *rcv_local_ids,
+                      int index_base, gsb_plan_t *out);
+/* dst(own, destination layout) <- src(own, source layout) through a redistribution plan */
+int gsb_vec_redistribute(gsb_plan_t plan, gsb_vec_t src, gsb_vec_t dst);
 
 /* ---------------------------------------------------------------- PSparseMatrix mirror
  * Local block of partition(A): n_rows own rows x (n_own_cols + n_ghost_cols) local columns in
@@ -176,6 +191,15 @@ int gsb_gmg_create(gsb_ctx_t ctx, int nlev, const gsb_mat_t *mats, const gsb_mat
                    const gsb_mat_t *restrict_, const gsb_solver_t *pre, const gsb_solver_t *post,
                    gsb_solver_t coarsest, int mode, int cycle_type, int maxiter, double atol, double rtol,
                    gsb_solver_t *out);
+/* GMG whose coarse levels live on fewer parts (ModelHierarchy np_per_level; GridTransferOperators.jl:391-401,536-561 with
+ * redist = Val{true}): to_coarse[l] / to_fine[l] (nlev-1 entries, NULL = level l+2 lives on the parts of level l+1) are
+ * redistribution plans between the row layout of restrict[l] / the column layout of interp[l] (coarse space in the
+ * partition of the finer level's parts) and the layout of mats[l+1].  Ranks that do not hold a level pass empty
+ * (zero-row) matrices for it; every rank still makes every call (the collectives are global). */
+int gsb_gmg_create_redist(gsb_ctx_t ctx, int nlev, const gsb_mat_t *mats, const gsb_mat_t *interp,
+                          const gsb_mat_t *restrict_, const gsb_solver_t *pre, const gsb_solver_t *post,
+                          gsb_solver_t coarsest, int mode, int cycle_type, int maxiter, double atol, double rtol,
+                          const gsb_plan_t *to_coarse, const gsb_plan_t *to_fine, gsb_solver_t *out);
 /* CGSolver(Pl;maxiter,atol,rtol,flexible), Krylov/CGSolvers.jl:10-120.  Pl may be NULL. */
 int gsb_cg_create(gsb_mat_t A, gsb_solver_t Pl, int flexible, int maxiter, double atol, double rtol,
                   gsb_solver_t *out);

@@ -5,6 +5,9 @@ Checks, through the C ABI over NCCL:
   2. distributed SpMV == oracle CSR mul on the local block (own-first column order) bit-exactly, and
      == the serial product up to rounding
   3. distributed GMG-PCG (V-cycle) iteration count and residual history == serial oracle solve (1e-10)
+  4. the NCCL send/recv halo path gives the same bits as the peer-memory path
+  5. levels on fewer parts (np_per_level): redistribute! round trip is exact, and GMG-PCG with the two coarsest levels
+     agglomerated on rank 0 reproduces the serial oracle's history (1e-10)
 """
 import os
 import sys
@@ -56,7 +59,7 @@ def main():
     # 2. SpMV (the "auto" runs use the own/ghost split with the halo exchange overlapped on a second stream)
     ctx.set_option("overlap", "1")
     ctx.set_option("overlap_min_rows", os.environ.get("MGPU_OVERLAP_MIN_ROWS", "1"))
-    for kern in ("auto", "sell", "stream", "vector"):
+    for kern in ("auto", "vector"):  # block-SELL row kernel (interior / boundary split) and the CSR fallback kernel
         ctx.set_option("spmv", kern)
         y = gsb.allocate_in_range(A)
         x.set(xg[gid[: lp.n_own]])
@@ -113,6 +116,58 @@ def main():
     gsb.mul_(y2, A2, x2)
     assert np.array_equal(y2.get(), yo), "NCCL halo path differs"
     ctx.set_option("p2p", "1")
+    dist.barrier()
+
+    # 5. levels on fewer parts: 4 levels, the two coarsest on rank 0 only
+    nlev2 = 4
+    one = (1,) * len(parts)
+    ppl = [parts, parts, one, one]
+    hh2 = synth.poisson_hierarchy_host(ncell, nlev2, parts=parts, rank=rank, lengths=lengths, parts_per_level=ppl)
+    dh2 = synth.upload_hierarchy(ctx, hh2)
+    assert dh2.redist is not None and (hh2.levels[2].n_own > 0) == (rank == 0)
+    #    redistribute there and back: own values of the level-3 coarse space in the partition of level 2's parts
+    cr = hh2.coarse_red[1]
+    gcr = synth.lexicographic_ids(cr)
+    N3 = int(np.prod([c // 4 - 1 for c in ncell]))
+    zg = np.cos(np.arange(N3, dtype=np.float64))
+    src = gsb.Vector(ctx, cr.n_own)
+    src.set(zg[gcr[: cr.n_own]])
+    agg = gsb.Vector(ctx, hh2.levels[2].n_own)
+    gsb.redistribute_(agg, dh2.to_coarse[1], src)
+    if rank == 0:
+        assert np.array_equal(agg.get(), zg), "redistribute to the agglomerated level is not the serial vector"
+    back = gsb.Vector(ctx, cr.n_own)
+    gsb.redistribute_(back, dh2.to_fine[1], agg)
+    assert np.array_equal(back.get(), zg[gcr[: cr.n_own]]), "redistribute round trip"
+    sm2 = gsb.Fill(gsb.RichardsonSmoother(gsb.JacobiLinearSolver(), 10, 2.0 / 3.0), nlev2 - 1)
+    gmg2 = gsb.GMGLinearSolver(dh2.A, dh2.P, dh2.R, pre_smoothers=sm2, post_smoothers=sm2, maxiter=1, redist=dh2.redist)
+    s2 = gsb.CGSolver(gmg2, maxiter=30, atol=1e-14, rtol=1e-8)
+    A2 = dh2.A[0]
+    ns2 = gsb.numerical_setup(gsb.symbolic_setup(s2, A2), A2)
+    xs2, b2 = gsb.allocate_in_domain(A2), gsb.allocate_in_domain(A2)
+    b2.set(hh2.b)
+    hist2 = None
+    for _ in range(3):  # eager, captured, replayed
+        xs2.fill(0.0)
+        gsb.solve_(xs2, ns2, b2)
+        if hist2 is None:
+            hist2 = s2.log.history()
+        assert np.array_equal(s2.log.history(), hist2), "graph replay changes the history of the agglomerated GMG"
+    err2 = float(np.max(np.abs(xs2.get() - synth.exact_solution(hh2.levels[0]))))
+    if rank == 0:
+        hs2 = synth.poisson_hierarchy_host(ncell, nlev2, lengths=lengths)
+        mats2, P2, R2 = oracle_hierarchy(hs2)
+        smo2 = [OS.RichardsonSmoother(OS.JacobiLinearSolver(), 10, 2.0 / 3.0)] * (nlev2 - 1)
+        go2 = OS.GMGLinearSolver(mats2, P2, R2, pre_smoothers=smo2, post_smoothers=smo2, maxiter=1)
+        so2 = OS.CGSolver(go2, maxiter=30, atol=1e-14, rtol=1e-8)
+        xo2 = np.zeros(mats2[0].shape[0])
+        OS.solve_(xo2, OS.numerical_setup(OS.symbolic_setup(so2, mats2[0]), mats2[0]), hs2.b)
+        dd2 = rel_hist_diff(hist2, so2.log.history())
+        assert s2.log.num_iters == so2.log.num_iters, (s2.log.num_iters, so2.log.num_iters)
+        assert dd2 < 1e-10, dd2
+        print(f"mgpu_check agglomerated ok: world={world} levels on parts {ppl} iters={s2.log.num_iters} hist_diff={dd2:.2e} "
+              f"max_err={err2:.2e}", flush=True)
+    assert err2 < 1e-7
     dist.barrier()
     dist.destroy_process_group()
 

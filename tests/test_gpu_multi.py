@@ -25,4 +25,4 @@ def test_distributed_parity(world, cells):
            "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert "mgpu_check ok" in out.stdout
+    assert "mgpu_check ok" in out.stdout and "mgpu_check agglomerated ok" in out.stdout

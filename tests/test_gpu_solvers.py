@@ -286,3 +286,44 @@ def test_schur_complement_solver(gsb, ctx):
     gsb.solve_(xd, ns, yd)
     M = sp.bmat([[Au, Bt], [B, D]], format="csr")
     assert np.linalg.norm(M @ xd.get() - y) <= 1e-9 * np.linalg.norm(y)
+
+
+def test_redistribution_plan_single_part_and_gmg_with_redistributed_level(gsb, ctx):
+    """gsb_redist_create / gsb_vec_redistribute on one part (a permutation of own values) and GMG built through
+    gsb_gmg_create_redist with identity plans on one level boundary: the redistributed V-cycle must reproduce the plain
+    one bit for bit (the multi-rank case runs in tests/mgpu_check.py)"""
+    from gsb200 import synth
+
+    n = 1000
+    perm = np.random.default_rng(5).permutation(n).astype(np.int64)
+    plan = gsb.RedistributionPlan(ctx, n, n, [0], [0, n], np.arange(n), [0], [0, n], perm)
+    x = np.random.default_rng(6).standard_normal(n)
+    src, dst = gsb.Vector(ctx, n), gsb.Vector(ctx, n)
+    src.set(x)
+    gsb.redistribute_(dst, plan, src)
+    out = np.empty(n)
+    out[perm] = x
+    assert np.array_equal(dst.get(), out)
+    with pytest.raises(gsb.GSBError):
+        gsb.redistribute_(gsb.Vector(ctx, n + 1), plan, src)
+    nlev = 3
+    hh = synth.poisson_hierarchy_host((16, 16, 16), nlev)
+    dh = synth.upload_hierarchy(ctx, hh)
+    hists = []
+    for use_redist in (False, True):
+        redist = None
+        if use_redist:
+            n2 = hh.levels[2].n_own
+            ident = lambda: gsb.RedistributionPlan(ctx, n2, n2, [0], [0, n2], np.arange(n2), [0], [0, n2], np.arange(n2))
+            redist = ([None, ident()], [None, ident()])
+        sm = gsb.Fill(gsb.RichardsonSmoother(gsb.JacobiLinearSolver(), 5, 2.0 / 3.0), nlev - 1)
+        gmg = gsb.GMGLinearSolver(dh.A, dh.P, dh.R, pre_smoothers=sm, post_smoothers=sm, maxiter=1, redist=redist)
+        s = gsb.CGSolver(gmg, maxiter=30, atol=1e-14, rtol=1e-8)
+        ns = gsb.numerical_setup(gsb.symbolic_setup(s, dh.A[0]), dh.A[0])
+        xs, b = gsb.allocate_in_domain(dh.A[0]), gsb.allocate_in_domain(dh.A[0])
+        b.set(hh.b)
+        for _ in range(2):
+            xs.fill(0.0)
+            gsb.solve_(xs, ns, b)
+        hists.append(s.log.history())
+    assert np.array_equal(hists[0], hists[1])

@@ -138,6 +138,79 @@ def test_transfer_operators_distributed_match_serial():
     assert abs(Rg.tocsr() - H.R[0]).max() == 0.0
 
 
+@pytest.mark.parametrize("nc,src,dst", [((16, 8, 8), (2, 1, 1), (1, 1, 1)), ((8, 8, 8), (2, 2, 2), (1, 1, 1)),
+                                        ((8, 8, 8), (2, 2, 2), (2, 1, 1)), ((8, 8, 8), (1, 1, 1), (2, 2, 1))])
+def test_redistribution_lists_move_every_own_value_once(nc, src, dst):
+    """RedistributionOperator data for Cartesian partitions (GridTransferOperators.jl:447-532): what p sends to q is what
+    q expects from p, in the same order; applying the lists to the distributed pieces of a global vector yields the
+    pieces of the same vector in the destination partition; ranks beyond the destination grid end up empty"""
+    nranks = max(int(np.prod(src)), int(np.prod(dst)))
+    L = [synth.redistribution_lists(nc, src, dst, r) for r in range(nranks)]
+    sp_ = [synth.level_part_or_empty(nc, src, r) for r in range(nranks)]
+    dp_ = [synth.level_part_or_empty(nc, dst, r) for r in range(nranks)]
+    N = int(np.prod([n - 1 for n in nc]))
+    xg = np.cos(np.arange(N, dtype=np.float64))
+    gs = [synth.lexicographic_ids(lp)[: lp.n_own] if lp.n_own else np.zeros(0, dtype=np.int64) for lp in sp_]
+    gd = [synth.lexicographic_ids(lp)[: lp.n_own] if lp.n_own else np.zeros(0, dtype=np.int64) for lp in dp_]
+    out = [np.full(lp.n_own, np.nan) for lp in dp_]
+    for p_, (ns, nd, nbs, sptr, sids, nbr, rptr, rids) in enumerate(L):
+        assert ns == sp_[p_].n_own and nd == dp_[p_].n_own
+        assert sptr[-1] == ns and rptr[-1] == nd  # every own value leaves once, every own slot is filled once
+        assert np.array_equal(np.sort(sids), np.arange(ns)) and np.array_equal(np.sort(rids), np.arange(nd))
+        for k, q_ in enumerate(nbs):
+            sent = sids[sptr[k]:sptr[k + 1]]
+            nq = L[q_]
+            kk = list(nq[5]).index(p_)
+            slots = nq[7][nq[6][kk]:nq[6][kk + 1]]
+            assert np.array_equal(gs[p_][sent], gd[q_][slots])  # same global dofs, same order
+            out[q_][slots] = xg[gs[p_][sent]]
+    for r in range(nranks):
+        assert np.array_equal(out[r], xg[gd[r]])
+        if r >= int(np.prod(dst)):
+            assert dp_[r].n_own == 0
+
+
+def test_hierarchy_with_levels_on_fewer_parts_matches_serial_transfers():
+    """np_per_level semantics: the two finest levels on 2x2x1 parts, the coarse ones on one part.  Across the boundary
+    the restriction acts in the partition of the finer level and is followed by the redistribution (and the prolongation
+    preceded by the reverse one): together they reproduce the serial R x and P x"""
+    nc, parts, nlev = (16, 16, 8), (2, 2, 1), 3
+    ppl = [parts, parts, (1, 1, 1)]
+    H = fem.poisson_hierarchy(nc, nlev)
+    hhs = [synth.poisson_hierarchy_host(nc, nlev, parts=parts, rank=r, parts_per_level=ppl) for r in range(4)]
+    for r, hh in enumerate(hhs):
+        assert hh.coarse_red[0] is None and hh.coarse_red[1] is not None
+        assert (hh.levels[2].n_own > 0) == (r == 0)  # the coarsest level lives on rank 0 only
+        if r == 0:  # ... where it is the serial matrix in the serial ordering
+            A2 = synth.to_scipy(*hh.A[2], hh.levels[2].n_own)
+            assert abs(A2 - H.mats[2]).max() < 1e-14
+    # restriction from level 2 (distributed) to level 3 (rank 0): y = redistribute(R_local x_local)
+    N1, N2 = H.mats[1].shape[0], H.mats[2].shape[0]
+    x1 = np.sin(1.0 + np.arange(N1, dtype=np.float64))
+    y_ref = H.R[1] @ x1
+    y0 = np.full(N2, np.nan)
+    z2 = np.cos(np.arange(N2, dtype=np.float64))
+    p_ref = H.P[1] @ z2
+    p_out = np.full(N1, np.nan)
+    for r, hh in enumerate(hhs):
+        f, cr = hh.levels[1], hh.coarse_red[1]
+        gf, gc = synth.lexicographic_ids(f), synth.lexicographic_ids(cr)
+        yl = synth.to_scipy(*hh.R[1], f.n_own + f.n_ghost) @ x1[gf]           # own rows of the redistributed coarse space
+        ns, nd, nbs, sptr, sids, nbr, rptr, rids = hh.to_coarse[1]
+        assert list(nbs) == [0] and ns == cr.n_own                            # everything goes to rank 0
+        k0 = list(hhs[0].to_coarse[1][5]).index(r)
+        slots = hhs[0].to_coarse[1][7][hhs[0].to_coarse[1][6][k0]:hhs[0].to_coarse[1][6][k0 + 1]]
+        y0[slots] = yl[sids]
+        # prolongation: rank 0 scatters z2 (its own, serial order) to the redistributed layout, ghosts filled, P applied
+        zl = z2[gc]                                                            # what redistribute + consistent! deliver
+        pl = synth.to_scipy(*hh.P[1], cr.n_own + cr.n_ghost) @ zl
+        p_out[gf[: f.n_own]] = pl
+        ns2, nd2, nbs2, sptr2, sids2, nbr2, rptr2, rids2 = hh.to_fine[1]
+        assert nd2 == cr.n_own and (list(nbr2) == [0] if cr.n_own else True)
+    assert np.abs(y0 - y_ref).max() <= 1e-14 * np.abs(y_ref).max()
+    assert np.abs(p_out - p_ref).max() <= 1e-14 * np.abs(p_ref).max()
+
+
 def _gloo_worker(rank, world, nc, parts, port, q):
     import torch
     import torch.distributed as dist
