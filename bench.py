@@ -361,7 +361,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scaling-base", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
-    ap.add_argument("--agglomerate-rows", type=int, default=int(os.environ.get("GSB_BENCH_AGGLOMERATE_ROWS", "5000")),
+    ap.add_argument("--agglomerate-rows", type=int, default=int(os.environ.get("GSB_BENCH_AGGLOMERATE_ROWS", "40000")),
                     help="N>1: GMG levels with at most this many rows per GPU live on rank 0 only (0 = every level on every GPU)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
