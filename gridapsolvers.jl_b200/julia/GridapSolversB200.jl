@@ -19,6 +19,8 @@ using PartitionedArrays
 using GridapSolvers
 using GridapSolvers.LinearSolvers
 using GridapSolvers.SolverInterfaces
+using GridapSolvers.BlockSolvers
+using BlockArrays
 import MPI
 
 const libgsb = get(ENV, "GSB200_LIB", "libgsb200.so")
@@ -54,6 +56,15 @@ mutable struct B200Matrix
   own_to_local::Vector{Int}      # to move values between Julia's local numbering and own-first numbering
   ghost_to_local::Vector{Int}
   ctx::B200Context
+  own_rows::Vector{Int}          # local ids of the own rows (PSparseMatrix parts; empty for serial matrices)
+  l2new::Vector{Int}             # Julia local column numbering -> own-first numbering
+end
+B200Matrix(h, plan, o2l, g2l, ctx) = B200Matrix(h, plan, o2l, g2l, ctx, Int[], Int[])
+
+"values of one part in the order the device matrix was created with (same sparsity => same order)"
+function _own_first_values(Al::SparseMatrixCSC, own_rows::Vector{Int}, l2new::Vector{Int}, n_cols::Int)
+  I, J, V = findnz(Al[own_rows, :])
+  return sparse(I, l2new[J], V, length(own_rows), n_cols).nzval
 end
 
 "Serial matrix: SparseMatrixCSC{Float64,Int64}, 1-based, passed untouched (fmt = CSC)."
@@ -101,7 +112,7 @@ function B200Matrix(ctx::B200Context, A::PSparseMatrix)
     check(ccall((:gsb_mat_create, libgsb), Cint,
       (Ptr{Cvoid}, Int64, Int64, Int64, Cint, Cint, Cint, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}),
       ctx.h, size(B,1), n_own, n_ghost, 1, 1, 8, B.colptr, B.rowval, B.nzval, plan[], h))
-    B200Matrix(h[], plan[], collect(o2l), collect(g2l), ctx)
+    B200Matrix(h[], plan[], collect(o2l), collect(g2l), ctx, collect(own_to_local(ri)), l2new)
   end |> PartitionedArrays.getany   # one part per process under with_mpi
 end
 
@@ -234,6 +245,17 @@ function Gridap.Algebra.numerical_setup!(ns::B200NumericalSetup, A::SparseMatrix
   check(ccall((:gsb_solver_update, libgsb), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), ns.h, ns.A.h))
   return ns
 end
+"numerical_setup!(ns,A) for a PSparseMatrix with the sparsity ns was built with: the own rows of every part are
+re-extracted in the creation order (own-first columns, CSC) and uploaded as values only."
+function Gridap.Algebra.numerical_setup!(ns::B200NumericalSetup, A::PSparseMatrix)
+  map(partition(A)) do Al
+    vals = _own_first_values(Al, ns.A.own_rows, ns.A.l2new, length(ns.A.own_to_local) + length(ns.A.ghost_to_local))
+    check(ccall((:gsb_mat_update_values, libgsb), Cint, (Ptr{Cvoid}, Ptr{Float64}), ns.A.h, vals))
+  end
+  check(ccall((:gsb_solver_update, libgsb), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), ns.h, ns.A.h))
+  return ns
+end
+Gridap.Algebra.numerical_setup!(ns::B200NumericalSetup, A::AbstractMatrix, x::AbstractVector) = numerical_setup!(ns, A)  # GridapExtras.jl:11-13
 
 function _fill_logs!(ns::B200NumericalSetup)
   for (log, h) in ns.logs
@@ -263,6 +285,92 @@ function Gridap.Algebra.solve!(x::PVector, ns::B200NumericalSetup, b::PVector)
   return x
 end
 LinearAlgebra.ldiv!(x, ns::B200NumericalSetup, b) = solve!(x, ns, b)
+
+# The AffineOperator entry points of src/SolverInterfaces/GridapExtras.jl:33-58, spelled out for B200Solver (the
+# reference's generic methods for ::LinearSolver would dispatch here as well): `x` may carry the FE-space ghost
+# layout, the solve runs on a vector with the layout of the matrix' columns, ghosts of x are made consistent.
+function Gridap.Algebra.solve!(x::PVector, ls::B200Solver, op::Gridap.Algebra.AffineOperator, cache::Nothing)
+  A, b = op.matrix, op.vector
+  ns = numerical_setup(symbolic_setup(ls, A), A)
+  y = allocate_in_domain(A)
+  copy!(y, x)
+  solve!(y, ns, b)
+  copy!(x, y)
+  consistent!(x) |> wait
+  return ns, y
+end
+function Gridap.Algebra.solve!(x::PVector, ls::B200Solver, op::Gridap.Algebra.AffineOperator, cache, newmatrix::Bool)
+  A, b = op.matrix, op.vector
+  ns, y = cache
+  newmatrix && numerical_setup!(ns, A)
+  copy!(y, x)
+  solve!(y, ns, b)
+  copy!(x, y)
+  consistent!(x) |> wait
+  return cache
+end
+
+# ------------------------------------------------------------------ block systems (BlockSolvers/)
+"Serial block matrix (BlockArrays.BlockMatrix of SparseMatrixCSC): one device matrix per non-zero block + the block
+matrix that acts on concatenated vectors (usable as the A of the Krylov solvers)."
+struct B200BlockMatrix
+  h::Ptr{Cvoid}
+  blocks::Matrix{Union{Nothing,B200Matrix}}
+  ctx::B200Context
+end
+function B200BlockMatrix(ctx::B200Context, A::BlockArrays.AbstractBlockMatrix)
+  nb = blocksize(A, 1)
+  @assert nb == blocksize(A, 2)
+  bl = Matrix{Union{Nothing,B200Matrix}}(nothing, nb, nb)
+  for i in 1:nb, j in 1:nb
+    Aij = A[Block(i, j)]
+    nnz(Aij) > 0 && (bl[i, j] = B200Matrix(ctx, SparseMatrixCSC{Float64,Int64}(Aij)))
+  end
+  hb = Ptr{Cvoid}[isnothing(bl[i, j]) ? C_NULL : bl[i, j].h for i in 1:nb for j in 1:nb]   # row-major
+  h = _create(:gsb_block_mat_create, (Ptr{Cvoid}, Cint, Ptr{Ptr{Cvoid}}), ctx.h, nb, hb)
+  return B200BlockMatrix(h, bl, ctx)
+end
+"BlockTriangularSolver / BlockDiagonalSolver whose blocks are LinearSystemBlocks (taken from the system matrix;
+BlockTriangularSolvers.jl:26-58, BlockDiagonalSolvers.jl:22-60).  Matrix/Biform blocks: build the block with the
+reference on the host, upload it with B200Matrix and call device_block_triangular directly."
+function device_ns(s::BlockSolvers.BlockTriangularSolver{Val{H}}, A::B200BlockMatrix, reg) where H
+  all(b -> b isa BlockSolvers.LinearSystemBlock, s.blocks) || error("B200: only LinearSystemBlock blocks are dispatched automatically")
+  device_block_triangular(A.ctx, A.blocks, collect(s.solvers), Matrix{Float64}(s.coeffs), H, reg)
+end
+function device_ns(s::BlockSolvers.BlockDiagonalSolver, A::B200BlockMatrix, reg)
+  all(b -> b isa BlockSolvers.LinearSystemBlock, s.blocks) || error("B200: only LinearSystemBlock blocks are dispatched automatically")
+  nb = length(s.solvers)
+  hs = Ptr{Cvoid}[device_ns(s.solvers[i], A.blocks[i, i], reg) for i in 1:nb]
+  hb = Ptr{Cvoid}[(i == j && !isnothing(A.blocks[i, j])) ? A.blocks[i, j].h : C_NULL for i in 1:nb for j in 1:nb]
+  _create(:gsb_block_solver_create, (Ptr{Cvoid}, Cint, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{Float64}, Cint, Cint),
+          A.ctx.h, nb, hb, hs, C_NULL, 0, 1)
+end
+# Krylov solvers on a block system: the operator is the block matrix, preconditioners see the blocks
+for (T, f) in ((:GMRESSolver, :gsb_gmres_create), (:FGMRESSolver, :gsb_fgmres_create))
+  @eval function device_ns(s::LinearSolvers.$T, A::B200BlockMatrix, reg)
+    Pr = device_ns(s.Pr, A, reg); Pl = device_ns(s.Pl, A, reg); t = s.log.tols
+    h = _create($(QuoteNode(f)), (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cint, Cint, Cdouble, Cdouble),
+                A.h, _h(Pr), _h(Pl), s.m, s.restart, s.m_add, t.maxiter, t.atol, t.rtol)
+    push!(reg, (s.log, h)); h
+  end
+end
+function Gridap.Algebra.numerical_setup(ss::B200SymbolicSetup, A::BlockArrays.AbstractBlockMatrix)
+  Ad  = B200BlockMatrix(ss.solver.ctx, A)
+  reg = Any[(:keepalive, Ad)]
+  h   = device_ns(ss.solver.solver, Ad, reg)
+  n   = size(A, 1)
+  mk() = (v = Ref{Ptr{Cvoid}}(); check(ccall((:gsb_vec_create, libgsb), Cint, (Ptr{Cvoid}, Int64, Int64, Ref{Ptr{Cvoid}}), Ad.ctx.h, n, 0, v)); B200Vector(v[], n))
+  A11 = first(b for b in Ad.blocks if !isnothing(b))
+  return B200NumericalSetup(ss.solver, A11, h, reg, mk(), mk())
+end
+"solve!(x,ns,b) for serial block vectors: the blocks are stored contiguously (BlockArrays' BlockedVector / mortar of Vectors)"
+function Gridap.Algebra.solve!(x::BlockArrays.AbstractBlockVector, ns::B200NumericalSetup, b::BlockArrays.AbstractBlockVector)
+  xf, bf = collect(x), collect(b)
+  check(ccall((:gsb_solve_host, libgsb), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64), ns.h, xf, bf, length(xf)))
+  copyto!(x, xf)
+  _fill_logs!(ns)
+  return x
+end
 
 """
 Materialise a transfer operator as a sparse matrix by probing `mul!(y,op,x)` with coloured 0/1 vectors
