@@ -147,6 +147,32 @@ def test_gmg_fgmres_w_f_cycles(gsb, ctx, cycle):
     assert rel_hist_diff(sg.log.history(), so.log.history()) < HIST_TOL
 
 
+def test_gmg_with_iterative_coarsest_solver_is_not_graph_captured(gsb, ctx):
+    """any LinearSolver is legal as coarsest solver (GMGLinearSolvers.jl:48-58).  A Krylov coarse solver reads scalars
+    back on the host every iteration, so the preconditioner application must NOT be captured into a CUDA graph
+    (capturable() guard): three consecutive solves on the same vector pair -- the pattern that triggers the capture --
+    keep returning the oracle's history"""
+    nc, nlev = (16, 16, 16), 3
+    hh = synth.poisson_hierarchy_host(nc, nlev)
+    dh = synth.upload_hierarchy(ctx, hh)
+    mats, P, R = oracle_hierarchy(hh)
+    mk = lambda S, m, p_, r_, sm: S.CGSolver(S.GMGLinearSolver(m, p_, r_, pre_smoothers=sm, post_smoothers=sm, maxiter=1,
+                                                               coarsest_solver=S.CGSolver(S.JacobiLinearSolver(), maxiter=200, atol=1e-14, rtol=1e-12)),
+                                             maxiter=20, atol=1e-14, rtol=1e-8)
+    sg = mk(gsb, dh.A, dh.P, dh.R, gsb.Fill(gsb.RichardsonSmoother(gsb.JacobiLinearSolver(), 10, 2.0 / 3.0), nlev - 1))
+    so = mk(OS, mats, P, R, [OS.RichardsonSmoother(OS.JacobiLinearSolver(), 10, 2.0 / 3.0)] * (nlev - 1))
+    xo = np.zeros(mats[0].shape[0])
+    OS.solve_(xo, OS.numerical_setup(OS.symbolic_setup(so, mats[0]), mats[0]), hh.b)
+    ns = gsb.numerical_setup(gsb.symbolic_setup(sg, dh.A[0]), dh.A[0])
+    xd, bd = dev_vec(gsb, dh.A[0]), dev_vec(gsb, dh.A[0], hh.b)
+    for _ in range(3):
+        xd.fill(0.0)
+        gsb.solve_(xd, ns, bd)
+        assert sg.log.num_iters == so.log.num_iters
+        assert rel_hist_diff(sg.log.history(), so.log.history()) < 1e-8  # inner CG to 1e-12: reduction-order noise amplified
+    assert np.linalg.norm(xd.get() - xo) <= 1e-7 * np.linalg.norm(xo)
+
+
 def test_gmg_solver_mode(gsb, ctx):
     hh = synth.poisson_hierarchy_host((16, 16), 3)
     dh = synth.upload_hierarchy(ctx, hh)
