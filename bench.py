@@ -36,8 +36,10 @@ if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
     os.environ["NCCL_DEBUG"] = "WARN"
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
-# part grids (px,py,pz): split the slowest-varying directions first so that halo faces are contiguous planes
-PARTS = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}
+# part grids (px,py,pz): only the slowest-varying directions are split, so that halo faces are contiguous planes AND
+# every mesh line (x direction) stays on one part: a split in x puts a ghost column at the end of every line, which
+# breaks the diagonal alignment of one slice in four/eight (measured: 105 ms instead of ~88 ms on 8 GPUs with 2x2x2)
+PARTS = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (1, 2, 4)}
 RTOL, ATOL, MAXITER = 1e-8, 1e-14, 100
 PER_ROW = {"spmv": 20, "spmv_dot": 28, "residual": 28, "sweep": 44, "spmv_add": 36}  # SURVEY.md 8d vector bytes per row
 
