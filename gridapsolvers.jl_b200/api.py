@@ -402,12 +402,23 @@ def set_solver_tolerances_(solver, maxiter=1000, atol=np.finfo(np.float64).eps, 
 
 
 class HierarchicalArray:
-    """MultilevelTools/HierarchicalArrays.jl:13-22: one entry per level plus the ranks taking part in it.  In this
-    build every level lives on every rank (no level redistribution yet), so `with_level` always runs `f`."""
+    """MultilevelTools/HierarchicalArrays.jl:13-22: one entry per level plus the ranks taking part in it.
+    `ranks[l]` is the collection of ranks that hold level l (None: every rank); on a rank outside it the entry is
+    `None` -- the reference's `nothing` -- and `map` / `with_level` skip it (HierarchicalArrays.jl:96-149).  The device
+    side of a level a rank does not hold is a zero-row matrix (synth.level_part_or_empty, gsb_gmg_create_redist)."""
 
-    def __init__(self, array, ranks=None):
+    def __init__(self, array, ranks=None, rank=0):
         self.array = list(array)
         self.ranks = list(ranks) if ranks is not None else [None] * len(self.array)
+        self.rank = rank
+        assert len(self.ranks) == len(self.array)
+        for l in range(len(self.array)):
+            if not self.i_am_in(l):
+                self.array[l] = None
+
+    def i_am_in(self, l) -> bool:  # GridapDistributed.i_am_in(ranks[l]) of this process
+        r = self.ranks[l]
+        return r is None or self.rank in r
 
     def __len__(self):
         return len(self.array)
@@ -421,14 +432,24 @@ class HierarchicalArray:
     def __iter__(self):
         return iter(self.array)
 
+    def map(self, f, *others):  # Base.map(f, args::HierarchicalArray...), HierarchicalArrays.jl:96-120
+        for o in others:
+            assert isinstance(o, HierarchicalArray) and o.ranks == self.ranks, "matching_level_parts"
+        out = [f(self.array[l], *[o.array[l] for o in others]) if self.i_am_in(l) else None for l in range(len(self))]
+        return HierarchicalArray(out, self.ranks, self.rank)
+
 
 def num_levels(a) -> int:  # HierarchicalArrays.jl:71
     return len(a)
 
 
-def with_level(f, a, lev, default=None):  # HierarchicalArrays.jl:139-149 (1-based level like the reference)
-    if lev < 1 or lev > len(a) or a[lev - 1] is None:
-        return default
+def with_level(f, a, lev, default=None):
+    """with_level(f, a, lev; default=nothing), HierarchicalArrays.jl:139-149 (1-based level like the reference): `default`
+    when this rank does not belong to the level's ranks; plain sequences always run `f`"""
+    if isinstance(a, HierarchicalArray):
+        if lev < 1 or lev > len(a) or not a.i_am_in(lev - 1):
+            return default
+        return f(a[lev - 1])
     return f(a[lev - 1])
 
 

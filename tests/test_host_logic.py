@@ -366,10 +366,18 @@ def test_two_rank_gloo_distributed_pcg_matches_serial_oracle():
 
 def test_host_mirror_plumbing():
     """HierarchicalArray / with_level / tolerances: host-only pieces of the reference interface"""
-    h = gsb200.HierarchicalArray(["A1", "A2", None])
-    assert gsb200.num_levels(h) == 3 and h[1] == "A2"
+    # levels on fewer parts (np_per_level = [4, 4, 1]): rank 2 does not hold level 3 (HierarchicalArrays.jl:96-149)
+    ranks = [None, range(4), [0]]
+    h = gsb200.HierarchicalArray(["A1", "A2", "A3"], ranks, rank=2)
+    assert gsb200.num_levels(h) == 3 and h[1] == "A2" and h[2] is None
     assert gsb200.with_level(lambda a: a + "!", h, 1) == "A1!"
     assert gsb200.with_level(lambda a: a, h, 3, default="skip") == "skip"  # rank not in the level
+    assert gsb200.with_level(lambda a: a, h, 3) is None
+    m = h.map(lambda a, b: a + b, gsb200.HierarchicalArray(["x", "y", "z"], ranks, rank=2))
+    assert m.array == ["A1x", "A2y", None] and m.ranks == ranks
+    h0 = gsb200.HierarchicalArray(["A1", "A2", "A3"], ranks, rank=0)
+    assert gsb200.with_level(lambda a: a, h0, 3, default="skip") == "A3"
+    assert gsb200.with_level(lambda a: a * 2, [1, 2, 3], 2) == 4  # plain arrays: every rank holds every level
     s = gsb200.CGSolver(maxiter=7)
     assert s.log.residuals.shape[0] == 8 and gsb200.get_solver_tolerances(s).maxiter == 7
     gsb200.set_solver_tolerances_(s, maxiter=12, rtol=1e-9)
