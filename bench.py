@@ -596,6 +596,13 @@ def main():
                                           f"{threads} OpenMP threads, scaled by {res['iters']}/{oit}"}
         line["parity"] = {"against": "CPU restatement (oracle/) on the same assembled system; first solve after set-up on both sides", "iterations_compared": oit,
                           "rel_residual_history_max_diff": d, "ok": bool(d < 1e-10)}
+    if world > 1:
+        # halo volume of one consistent! on the finest level (rank 0) against the NVLink roofline (900 GB/s per direction)
+        lp0 = prob.hh.levels[0]
+        snd = int(lp0.snd_ptrs[-1]) * 8
+        line["halo"] = {"level1_send_bytes_per_exchange_rank0": snd, "neighbours_rank0": int(len(lp0.nbr_snd)),
+                        "nvlink_time_at_900GBps_us": round(snd / 900e9 * 1e6, 2),
+                        "note": "an exchange costs 20-30 us end to end (DESIGN.md section 6): latency-bound, a few percent of the NVLink roofline"}
     if parity is not None:
         line["parity"] = parity
     if scaling_base is not None:
