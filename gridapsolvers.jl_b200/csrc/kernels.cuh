@@ -1,10 +1,12 @@
 // kernels.cuh -- hand-written sm_100a kernels of the gsb200 solve phase.
 //
-// Every kernel here is HBM-bandwidth bound: the design rules are perfectly
-// streamed matrix traffic (TMA bulk copies of the CSR value / column arrays into a shared-memory
-// ring, persistent CTAs), coalesced gathers of the input vector (one lane per row => the k-th
-// neighbours of consecutive rows are consecutive in memory on mesh-ordered matrices), fusion of
-// every elementwise epilogue into the row kernel, and deterministic two-stage reductions.
+// Every kernel here is HBM-bandwidth bound: the design rules are a matrix stream made of fully
+// coalesced 256 B lines whose addresses do not depend on row pointers (block-SELL-32, one lane per block row),
+// as few bytes per non-zero as the structure allows (column ids shared by DOF blocks and compressed to one word
+// per 32 blocks where the columns of a slice are consecutive), coalesced gathers of the input vector (the k-th
+// neighbours of 32 consecutive rows are 32 consecutive entries on a mesh-ordered matrix; runs of consecutive
+// columns are gathered once and shuffled), fusion of every elementwise epilogue into the row kernel, and
+// deterministic two-stage reductions.
 //
 // Rounding contract (DESIGN.md "parity"): a row sum is accumulated in ascending column order,
 // product rounded before the add (no FMA contraction) -- the sequence Julia's SparseArrays /
@@ -116,7 +118,7 @@ __device__ __forceinline__ void row_epilogue(const RowArgs &a, int64_t row, doub
 
 // ------------------------------------------------------------------------------------------
 // generic CSR kernel: G lanes per row, direct global loads.  Used for small levels (launch /
-// latency bound) and for matrices whose rows do not fit the streaming kernel's ring.
+// latency bound) and for matrices whose block-SELL padding would exceed the budget (matrix.cu plan_sell).
 template <int G, int MODE, int THREADS>
 __global__ void __launch_bounds__(THREADS) csr_vector_kernel(int64_t nrows, const int *__restrict__ rowptr,
                                                             const int *__restrict__ col,

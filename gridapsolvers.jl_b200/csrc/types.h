@@ -51,13 +51,7 @@ struct RowArgs {
 };
 
 
-struct StreamArgs {
-  const int *rowptr;
-  const int *col;       // padded to a multiple of 4 entries (16 B TMA granularity)
-  const double *val;    // idem
-  const int *cta_rows;  // gridDim.x + 1 row offsets
-  int64_t nnz_padded;   // multiple of 4
-};
+
 
 
 struct EwArgs {
