@@ -84,7 +84,7 @@ class ClockSampler:
             os.close(fd)
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -416,6 +416,9 @@ def main():
         mx = max_over_ranks if distributed else (lambda v: v)
         # ---- device-resident timing: inputs already in HBM
         hist_first = None
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()  # nvidia-smi needs ~50 ms to deliver its first sample: started before the warm-up solves (same load)
         for _ in range(warmup):
             x.fill(0.0)
             gsb.solve_(x, ns, b)
@@ -424,10 +427,7 @@ def main():
                 # iterative solvers from the previous solve's caches (reference quirk, BlockTriangularSolvers.jl:
                 # 188-242: the y caches are zeroed at set-up only), so later solves follow a different history
                 hist_first = solver.log.history()
-        sampler = ClockSampler(local_rank)
         sync()
-        if rank == 0:
-            sampler.start()
         l0 = c.launch_count()
         dev_ms, iters_seen = 0.0, []
         wall0 = time.perf_counter()
