@@ -517,6 +517,71 @@ def ldiv_(x, ns, b):
     return solve_(x, ns, b)
 
 
+class AffineOperator:
+    """Gridap.Algebra.AffineOperator: the pair (matrix, vector) a linear FE operator hands to the solver."""
+
+    def __init__(self, matrix, vector):
+        self.matrix, self.vector = matrix, vector
+
+
+def solve_affine_(x, ls, op: AffineOperator, cache=None, newmatrix: bool = False, plan=None):
+    """solve!(x::PVector, ls::LinearSolver, op::AffineOperator, cache[, newmatrix]) -- SolverInterfaces/GridapExtras.jl:33-58.
+    `x` may carry another ghost layout than the columns of op.matrix (an FE-space vector): the solve runs on a vector `y`
+    allocated in the domain of the matrix, own values are copied in and out, and the ghosts of `x` are made consistent
+    afterwards (`plan`: the exchange plan of x's layout; None on one part).  First call (cache None): symbolic +
+    numerical set-up, returns the cache (ns, y); later calls reuse it and refresh the set-up when newmatrix."""
+    A, b = op.matrix, op.vector
+    if cache is None:
+        ns = numerical_setup(symbolic_setup(ls, A), A)
+        y = allocate_in_domain(A)
+        cache = (ns, y)
+    else:
+        ns, y = cache
+        if newmatrix:
+            numerical_setup_(ns, A)
+    copy_(y, x)
+    solve_(y, ns, b)
+    copy_(x, y)
+    if plan is not None:
+        consistent_(x, plan)
+    return cache
+
+
+def explicit_transfer(mul, n_in: int, n_out: int, colour, ncolours: int):
+    """Materialise a linear transfer operator given only as `mul(y, x)` (y = op x on own values) as a scipy CSR matrix by
+    coloured probing -- the algorithm of `explicit_transfer` in julia/GridapSolversB200.jl (the reference's GMG accepts
+    any object with mul! as interp/restrict, GMGLinearSolvers.jl:484,491; setup_transfer_operators returns such
+    objects, GridTransferOperators.jl:350-401).  `colour(j)` in 0..ncolours-1 must differ for columns whose images
+    overlap (Q1, factor-2 refinement: 2^d colours on the coarse node grid; 3^d for the restriction).  Two probes per
+    colour: x = 1 on the colour's columns gives the values, x = column id gives the column of every non-zero row."""
+    import scipy.sparse as sp
+
+    cols_of = [[] for _ in range(ncolours)]
+    for j in range(n_in):
+        cols_of[colour(j)].append(j)
+    I, J, V = [], [], []
+    x, y, y2 = np.zeros(n_in), np.zeros(n_out), np.zeros(n_out)
+    for cols in cols_of:
+        if not cols:
+            continue
+        cols = np.asarray(cols)
+        x[:] = 0.0
+        x[cols] = 1.0
+        mul(y, x)
+        x[cols] = cols + 1.0  # 1-based ids: column 0 stays distinguishable from "no contribution"
+        mul(y2, x)
+        rows = np.flatnonzero(y)
+        q = y2[rows] / y[rows]
+        if np.any(np.abs(q - np.rint(q)) > 1e-6):
+            raise ValueError("explicit_transfer: two columns of one colour overlap (invalid colouring)")
+        I.append(rows)
+        J.append(np.rint(q).astype(np.int64) - 1)
+        V.append(y[rows].copy())
+    if not I:
+        return sp.csr_matrix((n_out, n_in))
+    return sp.csr_matrix((np.concatenate(V), (np.concatenate(I), np.concatenate(J))), shape=(n_out, n_in))
+
+
 def _child(solver, A):
     return None if solver is None else numerical_setup(symbolic_setup(solver, A), A)
 

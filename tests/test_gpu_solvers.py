@@ -353,3 +353,28 @@ def test_redistribution_plan_single_part_and_gmg_with_redistributed_level(gsb, c
             gsb.solve_(xs, ns, b)
         hists.append(s.log.history())
     assert np.array_equal(hists[0], hists[1])
+
+
+def test_solve_affine_operator_entry_points(gsb, ctx):
+    """solve!(x, ls, op::AffineOperator, cache[, newmatrix]) -- SolverInterfaces/GridapExtras.jl:33-58: first call sets up
+    and returns the cache (ns, y); later calls reuse it, newmatrix=True refreshes the numerical set-up after the values
+    of the matrix changed; x is only touched through own-value copies"""
+    sysm = fem.poisson((24, 24))
+    A = dev_matrix(gsb, ctx, sysm.A)
+    b = dev_vec(gsb, A, sysm.b)
+    op = gsb.AffineOperator(A, b)
+    ls = gsb.CGSolver(gsb.JacobiLinearSolver(), maxiter=500, atol=1e-14, rtol=1e-10)
+    x = dev_vec(gsb, A)
+    cache = gsb.solve_affine_(x, ls, op)
+    so = OS.CGSolver(OS.JacobiLinearSolver(), maxiter=500, atol=1e-14, rtol=1e-10)
+    Ao = ola.CSR(sysm.A)
+    xo = np.zeros(sysm.A.shape[0])
+    OS.solve_(xo, OS.numerical_setup(OS.symbolic_setup(so, Ao), Ao), sysm.b)
+    assert ls.log.num_iters == so.log.num_iters and rel_hist_diff(ls.log.history(), so.log.history()) < HIST_TOL
+    assert np.linalg.norm(x.get() - xo) <= 1e-9 * np.linalg.norm(xo)
+    # same cache, new matrix values (2 A): the solution halves, the set-up objects are reused
+    A.update_values(2.0 * sysm.A.data)  # same sparsity, new values
+    x.fill(0.0)
+    cache2 = gsb.solve_affine_(x, ls, op, cache, newmatrix=True)
+    assert cache2 is cache
+    assert np.linalg.norm(x.get() - 0.5 * xo) <= 1e-8 * np.linalg.norm(xo)

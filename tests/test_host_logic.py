@@ -391,6 +391,35 @@ def test_host_mirror_plumbing():
         gsb200.GMGLinearSolver([1, 2, 3], [1], [1, 2])
 
 
+def test_explicit_transfer_by_coloured_probing():
+    """setup_transfer_operators hands the GMG objects that only support mul! (GridTransferOperators.jl:350-401); the
+    shim materialises them by coloured probing (julia/GridapSolversB200.jl explicit_transfer, mirrored in api.py).
+    Probing the oracle's prolongation / restriction through mul only recovers the matrices exactly: 2^d colours on the
+    coarse node grid for P, 3^d on the fine grid for R = P'; an invalid colouring is detected"""
+    nc = (8, 8, 8)
+    H = fem.poisson_hierarchy(nc, 2)
+    P, R = H.P[0], H.R[0]
+    nf, ncs = tuple(n - 1 for n in nc), tuple(n // 2 - 1 for n in nc)  # free nodes per direction, lexicographic (x fastest)
+
+    def coords(j, dims):
+        out = []
+        for n in dims:
+            out.append(j % n)
+            j //= n
+        return out
+
+    colour_c = lambda j: sum((c % 2) << k for k, c in enumerate(coords(j, ncs)))
+    colour_f = lambda j: sum((c % 3) * 3 ** k for k, c in enumerate(coords(j, nf)))
+    mulP = lambda y, x: y.__setitem__(slice(None), P @ x)
+    mulR = lambda y, x: y.__setitem__(slice(None), R @ x)
+    Pp = gsb200.explicit_transfer(mulP, P.shape[1], P.shape[0], colour_c, 8)
+    Rp = gsb200.explicit_transfer(mulR, R.shape[1], R.shape[0], colour_f, 27)
+    assert abs(Pp - P).max() == 0.0 and Pp.nnz == P.nnz
+    assert abs(Rp - R).max() == 0.0 and abs(Rp - Pp.T).max() <= 1e-15
+    with pytest.raises(ValueError):
+        gsb200.explicit_transfer(mulP, P.shape[1], P.shape[0], lambda j: 0, 1)
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (CPU oracle port) prints one JSON line with the contract's keys"""
     import json
