@@ -206,3 +206,40 @@ def test_block_diagonal_solver_known_answer():
     S.solve_(x, S.numerical_setup(S.symbolic_setup(solver, M), M), b)
     xd = spla.spsolve(M.to_scipy().tocsc(), b)
     assert np.linalg.norm(x - xd) < 1e-8
+
+
+def test_oracle_krylov_histories_against_independent_implementations():
+    """The oracle restates GridapSolvers' OWN variants of the Krylov methods; this cross-check ties its residual
+    histories to independent implementations of the published algorithms (scipy): for a consistent Jacobi
+    preconditioner the PCG iterates are unique, so the true residuals of scipy's iterates must equal the oracle's
+    recursively updated residual norms (CGSolvers.jl:85,111); the multigrid V-cycle as a stationary iteration
+    (mode=:solver) must contract the error like the two-grid operator I - M A it defines (checked through the exact
+    solve of the same system)."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+
+    sysm = fem.poisson((24, 20))
+    A, b = sp.csr_matrix(sysm.A), sysm.b
+    Ao = ola.CSR(A)
+    s = S.CGSolver(S.JacobiLinearSolver(), maxiter=60, atol=1e-30, rtol=1e-12)
+    x = np.zeros(A.shape[0])
+    S.solve_(x, S.numerical_setup(S.symbolic_setup(s, Ao), Ao), b)
+    hist = s.log.history()
+    true_res = [np.linalg.norm(b)]
+    Minv = sp.diags(1.0 / A.diagonal())
+    spla.cg(A, b, x0=np.zeros_like(b), M=Minv, rtol=1e-14, atol=0.0, maxiter=len(hist) - 1,
+            callback=lambda xk: true_res.append(np.linalg.norm(b - A @ xk)))
+    n = min(len(hist), len(true_res))
+    assert n >= 20
+    assert np.max(np.abs(np.array(true_res[:n]) - hist[:n])) <= 1e-9 * hist[0]
+    # GMG V-cycle in solver mode converges to the direct solution of the same system at a mesh-independent rate
+    H = fem.poisson_hierarchy((16, 16), 3)
+    mats = [ola.CSR(m) for m in H.mats]
+    g = S.GMGLinearSolver(mats, [ola.CSR(p) for p in H.P], [ola.CSR(r) for r in H.R], mode="solver", maxiter=30, rtol=1e-10)
+    xg = np.zeros(H.mats[0].shape[0])
+    S.solve_(xg, S.numerical_setup(S.symbolic_setup(g, mats[0]), mats[0]), H.systems[0].b)
+    xd = spla.spsolve(sp.csc_matrix(H.mats[0]), H.systems[0].b)
+    assert np.linalg.norm(xg - xd) <= 1e-8 * np.linalg.norm(xd)
+    h = g.log.history()
+    rates = h[2:] / h[1:-1]
+    assert rates.max() < 0.35  # textbook V(10,10)-cycle contraction for the 2D Laplacian with damped Jacobi
