@@ -541,7 +541,10 @@ def main():
                     "algorithmic_bytes_model": "SURVEY 8d: 12 B per non-zero (fp64 value + int32 column) + 44 B per row",
                     "format_bytes_per_launch": fbytes,
                     "format_GBps": round(fbytes / (top["avg_us"] * 1e-6) / 1e9, 1), "frac_format_bytes": round(fbytes / (top["avg_us"] * 1e-6) / 1e9 / peak, 4),
-                    "avg_launch_us": top["avg_us"], "traffic": None}
+                    "avg_launch_us": top["avg_us"], "traffic": None,
+                    "note": "achieved / frac use the ALGORITHMIC bytes of SURVEY 8d (CSR: 12 B per non-zero) as the measurement contract asks; the "
+                            "block-SELL format streams fewer bytes (format_bytes_per_launch, confirmed by the ncu DRAM `traffic`), so frac can exceed 1: "
+                            "the HBM utilisation of the kernel is frac_format_bytes"}
         tfile = os.path.join(ROOT, "profiles", "traffic_r02.json")
         if os.path.exists(tfile):
             try:
